@@ -1,0 +1,150 @@
+/* qsim_b200 -- C ABI of the B200-native gate-application engine.
+ *
+ * Drop-in boundary for the gate-application path of the reference's
+ * simulators/dv_simulator (abbreviated DV/ below).  The reference is pure
+ * Python/NumPy and has no FFI; each entry point replaces the NumPy routine
+ * cited beside it, and the Python shim in quantum_computations_b200/ binds the
+ * library with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - All functions return 0 on success, a negative QSIM_ERR_* otherwise, never
+ *    throw; qsim_last_error() returns a thread-local message.
+ *  - State buffers are BORROWED device pointers to interleaved (re, im) double
+ *    pairs (numpy/torch complex128), 2^n amplitudes, owned by the caller
+ *    (PyTorch).  Work is enqueued on the caller's cudaStream_t (passed as
+ *    void*); functions that return a scalar to the host synchronise that stream.
+ *  - Qubit numbers are the REFERENCE's: qubit 0 is the most significant bit of
+ *    the linear index (DV/numpy_quantum.py:243-247).  For a k-qubit matrix the
+ *    first tensor factor acts on targets[0] (DV/gates.py:116-126).
+ *  - Matrices are host pointers, row-major, interleaved complex128.
+ *  - A density matrix of N qubits is its row-major vec: a 2N-"qubit" buffer in
+ *    which row qubit q is qubit q and column qubit q is qubit q+N.
+ */
+#ifndef QSIM_B200_H
+#define QSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSIM_OK               0
+#define QSIM_ERR_ARG         -1   /* invalid argument                        */
+#define QSIM_ERR_CUDA        -2   /* a CUDA call failed                      */
+#define QSIM_ERR_UNSUPPORTED -3   /* valid request the library cannot serve  */
+#define QSIM_ERR_NOMEM       -4
+
+typedef struct qsim_circuit qsim_circuit_t;
+typedef struct qsim_plan qsim_plan_t;
+
+typedef struct {
+  int32_t tile_bits;        /* T: log2 amplitudes per shared-memory tile (<= 13); 0 = default  */
+  int32_t low_bits;         /* L: forced lowest index bits per tile (coalescing);  0 = default  */
+  int32_t max_group;        /* 2x2 gates fused per shared-memory round trip (1..4); 0 = default */
+  int32_t max_dense_ops;    /* cap on non-diagonal gates per pass;                 0 = default  */
+  int32_t lookahead;        /* gates scanned ahead when choosing a tile;           0 = default  */
+  int32_t merge_1q;         /* 0 = default (on), 1 = on, 2 = off                                */
+} qsim_plan_options_t;
+
+typedef struct {
+  int64_t n_input_ops;      /* gates handed to the circuit                                      */
+  int64_t n_merged_ops;     /* after single-qubit merging                                       */
+  int64_t n_passes;         /* tile passes (one HBM read+write of the state each)               */
+  int64_t n_steps;          /* shared-memory round trips over all passes                        */
+  int64_t n_dense;          /* matrix applications inside the steps                             */
+  int64_t n_sign;           /* CZ/Z sign pairs                                                  */
+  int64_t n_generic;        /* gates on > 4 qubits executed by the out-of-place generic kernel  */
+} qsim_plan_stats_t;
+
+const char* qsim_last_error(void);
+int qsim_version(void);
+/* 1 when the library was built with the CUDA kernels, 0 for the host emulator
+ * that the CPU tests build from the same planner sources. */
+int qsim_has_cuda(void);
+
+/* ---- circuits and fused plans: replace the per-gate loop of
+ *      Simulator.run (DV/simulator.py:40-52) -------------------------------- */
+int qsim_circuit_create(int n_qubits, qsim_circuit_t** out);
+/* Gate.apply ket branch, any k (DV/gates.py:48-50).  Structure (diagonal, CZ,
+ * Z) is detected from the matrix values. */
+int qsim_circuit_add_matrix(qsim_circuit_t* c, int k, const int* targets, const double* matrix);
+int qsim_circuit_num_ops(const qsim_circuit_t* c);
+void qsim_circuit_destroy(qsim_circuit_t* c);
+
+int qsim_plan_compile(const qsim_circuit_t* c, const qsim_plan_options_t* opt, qsim_plan_t** out);
+int qsim_plan_stats(const qsim_plan_t* p, qsim_plan_stats_t* out);
+/* scratch: device buffer of 2^n amplitudes, needed only when stats.n_generic > 0 */
+int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void* stream);
+void qsim_plan_destroy(qsim_plan_t* p);
+
+/* ---- single operations (each is a one-gate plan) ------------------------------- */
+/* expand_gate + `gate @ state` (DV/numpy_quantum.py:243-247, DV/gates.py:50) */
+int qsim_apply_matrix(void* state, int n_qubits, const int* targets, int k, const double* matrix,
+                      void* scratch, void* stream);
+/* same path for diagonal matrices (Z, RZ, P, Pdg, T, Tdg, CZ: DV/gates.py:79-130);
+ * diag holds the 2^k diagonal entries */
+int qsim_apply_diagonal(void* state, int n_qubits, const int* targets, int k, const double* diag,
+                        void* stream);
+/* same path for permutation matrices (X, CX, SWAP: DV/gates.py:71-73,116-134);
+ * column c of the matrix has its 1 in row perm[c] */
+int qsim_apply_permutation(void* state, int n_qubits, const int* targets, int k, const int* perm,
+                           void* stream);
+/* `gate @ rho @ dagger(gate)` (DV/gates.py:51-52) and Kraus sums
+ * (PAPER/tomography.py:21-24) as one 4^k x 4^k matrix on the vec of rho:
+ * targets are the k row qubits, the column qubits targets[i]+n are implied. */
+int qsim_apply_superop(void* vec_rho, int n_qubits, const int* targets, int k, const double* superop,
+                       void* scratch, void* stream);
+
+/* ---- state construction / register resizing -------------------------------------- */
+/* tensor(*(s.get() for s in states)) (DV/simulator.py:26); amps = n x 2 complex */
+int qsim_init_product(void* state, int n_qubits, const double* amps, void* stream);
+/* M.apply (DV/gates.py:165-186): out_norm2[s] = || (I..bra_s..I) psi ||^2 */
+int qsim_measure_probs(const void* state, int n_qubits, int qubit, const double* bra0,
+                       const double* bra1, double* out_norm2, void* stream);
+/* out (2^(n-1) amps) = (I..bra..I) in / norm   (DV/gates.py:185) */
+int qsim_collapse(const void* in, void* out, int n_qubits, int qubit, const double* bra, double norm,
+                  void* stream);
+/* Insert.apply (DV/gates.py:145-153): out has n+1 qubits, the new one at `position` */
+int qsim_insert(const void* in, void* out, int n_qubits, int position, const double* amp,
+                void* stream);
+
+/* ---- reductions (DV/numpy_quantum.py:131-166); results are host doubles ------------ */
+int qsim_reduce_norm2(const void* state, uint64_t n_amps, double* out, void* stream);
+int qsim_reduce_inner(const void* a, const void* b, uint64_t n_amps, double* out_re_im, void* stream);
+/* <ket| rho |ket> with rho a row-major 2^n x 2^n matrix */
+int qsim_reduce_expect(const void* ket, const void* rho, int n_qubits, double* out_re_im, void* stream);
+/* tr(rho rho) = sum_ij rho_ij rho_ji  (no Hermiticity assumed) */
+int qsim_reduce_purity(const void* rho, int n_qubits, double* out_re_im, void* stream);
+int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void* stream);
+
+/* ---- batched tiny-circuit executor (replaces the sample loop of
+ *      PAPER/randomised_benchmarking.py:65-75) --------------------------------------
+ * B independent registers of nq <= 2 qubits kept as density matrices (dim = 2^nq).
+ * Sequence b applies opcodes[offsets[b] .. offsets[b+1]); opcode o multiplies
+ * vec(rho) by superops[o] (dim^2 x dim^2) and the ideal ket by unitaries[o]
+ * (dim x dim).  Outputs per sequence: fidelity <psi|rho|psi> and purity tr rho^2.
+ * All pointers are DEVICE pointers except the scalar arguments. */
+int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets,
+                  int n_opcodes, const double* superops, const double* unitaries,
+                  const double* rho0, const double* psi0, double* out_fidelity, double* out_purity,
+                  double* out_rho, void* stream);
+
+/* ---- global<->local qubit swap helpers for sharded states -------------------------
+ * A state of n qubits sharded over 2^g ranks keeps reference qubits 0..g-1 in the
+ * rank number.  Exchanging global qubit qg with local qubit ql moves, on every rank,
+ * the half of the shard whose ql-bit differs from the rank's qg-bit.  These two
+ * kernels gather that half into a contiguous send buffer and scatter the received
+ * half back; the transfer itself is the caller's (NCCL send/recv or P2P copy). */
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit,
+                   void* stream);
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit,
+                     void* stream);
+
+/* Launch statistics since process start (kernels launched by this library). */
+int64_t qsim_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSIM_B200_H */

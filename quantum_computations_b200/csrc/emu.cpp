@@ -1,0 +1,295 @@
+// HOST EMULATOR -- TEST INFRASTRUCTURE ONLY.
+//
+// Builds (g++ only, no CUDA) into tests/_build/libqsim_emu.so and exports the
+// same C ABI as libqsim_b200.so, but on HOST pointers.  It runs the very same
+// planner (planner.cpp / capi_host.cpp) and the very same per-thread phase
+// functions (tile_exec.h, elem_ops.h) as the GPU kernels, looping over thread
+// ids where the GPU runs them in parallel.  The CPU test-suite uses it to check
+// the plan logic and the index arithmetic without a GPU.  The product package
+// never loads it: quantum_computations_b200.engine binds libqsim_b200.so only
+// and raises when that library or a CUDA device is missing.
+#include <cstring>
+#include <vector>
+
+#include "elem_ops.h"
+#include "planner.h"
+
+namespace {
+
+int64_t g_launches = 0;
+
+void emu_pass(const QsPass& P, qs_c128* state, int n) {
+  const uint64_t ntiles = 1ull << (n - (int)P.T);
+  std::vector<qs_c128> tile((size_t)1 << P.T);
+  std::vector<uint32_t> zmask(P.nsteps), gsign(P.nsteps);
+  const int nsteps = (int)P.nsteps;
+  for (uint64_t t = 0; t < ntiles; ++t) {
+    const uint64_t base = qs_tile_base(P, t);
+    for (int s = 0; s < nsteps; ++s) qs_sign_prepare(P, s, base, &zmask[s], &gsign[s]);
+    for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
+      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2);
+    for (int s = 0; s + 1 < nsteps; ++s)
+      for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
+        qs_phase_step_any<4>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
+    for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
+      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, zmask[nsteps - 1], gsign[nsteps - 1]);
+  }
+  ++g_launches;
+}
+
+int emu_generic(const qs::Op& op, qs_c128* state, qs_c128* scratch, int n) {
+  if (!scratch) return qs::fail(QSIM_ERR_ARG, "a gate on more than 4 qubits needs a scratch buffer of 2^n amplitudes");
+  const int dim = 1 << op.k;
+  std::vector<double> flat(2 * (size_t)dim * dim);
+  for (int e = 0; e < dim * dim; ++e) { flat[2 * e] = op.mat[e].real(); flat[2 * e + 1] = op.mat[e].imag(); }
+  int bits[10];
+  for (int f = 0; f < op.k; ++f) bits[f] = op.bits[f];
+  const uint64_t count = 1ull << n;
+  for (uint64_t i = 0; i < count; ++i) scratch[i] = qs_generic_amp(state, flat.data(), bits, op.k, i);
+  memcpy(state, scratch, sizeof(qs_c128) * count);
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int execute_plan(const qsim_plan* p, void* state, int n, void* scratch) {
+  if (!p || !state) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: null argument");
+  if (n != p->n) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: plan was compiled for a different qubit count");
+  for (const qs::PlanItem& it : p->items) {
+    if (it.generic) {
+      int rc = emu_generic(it.op, (qs_c128*)state, (qs_c128*)scratch, n);
+      if (rc != QSIM_OK) return rc;
+    } else {
+      if ((int)it.pass.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
+      emu_pass(it.pass, (qs_c128*)state, n);
+    }
+  }
+  return QSIM_OK;
+}
+
+int one_gate(void* state, int n, const int* targets, int k, const double* matrix, void* scratch) {
+  qsim_circuit_t* c = nullptr;
+  int rc = qsim_circuit_create(n, &c);
+  if (rc != QSIM_OK) return rc;
+  rc = qsim_circuit_add_matrix(c, k, targets, matrix);
+  qsim_plan_t* p = nullptr;
+  if (rc == QSIM_OK) rc = qsim_plan_compile(c, nullptr, &p);
+  if (rc == QSIM_OK) rc = execute_plan(p, state, n, scratch);
+  qsim_plan_destroy(p);
+  qsim_circuit_destroy(c);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qsim_has_cuda(void) { return 0; }
+int64_t qsim_launch_count(void) { return g_launches; }
+
+int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void*) {
+  return execute_plan(p, state, n_qubits, scratch);
+}
+
+int qsim_apply_matrix(void* state, int n_qubits, const int* targets, int k, const double* matrix,
+                      void* scratch, void*) {
+  if (!state || !targets || !matrix) return qs::fail(QSIM_ERR_ARG, "qsim_apply_matrix: null argument");
+  return one_gate(state, n_qubits, targets, k, matrix, scratch);
+}
+
+int qsim_apply_diagonal(void* state, int n_qubits, const int* targets, int k, const double* diag, void*) {
+  if (!state || !targets || !diag) return qs::fail(QSIM_ERR_ARG, "qsim_apply_diagonal: null argument");
+  if (k < 1 || k > QS_MAX_R) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_diagonal: k must be in [1, 4]");
+  const int dim = 1 << k;
+  std::vector<double> m(2 * (size_t)dim * dim, 0.0);
+  for (int d = 0; d < dim; ++d) { m[2 * (d * dim + d)] = diag[2 * d]; m[2 * (d * dim + d) + 1] = diag[2 * d + 1]; }
+  return one_gate(state, n_qubits, targets, k, m.data(), nullptr);
+}
+
+int qsim_apply_permutation(void* state, int n_qubits, const int* targets, int k, const int* perm, void*) {
+  if (!state || !targets || !perm) return qs::fail(QSIM_ERR_ARG, "qsim_apply_permutation: null argument");
+  if (k < 1 || k > QS_MAX_R) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_permutation: k must be in [1, 4]");
+  const int dim = 1 << k;
+  std::vector<double> m(2 * (size_t)dim * dim, 0.0);
+  std::vector<char> hit(dim, 0);
+  for (int c = 0; c < dim; ++c) {
+    if (perm[c] < 0 || perm[c] >= dim || hit[perm[c]]) return qs::fail(QSIM_ERR_ARG, "qsim_apply_permutation: not a permutation");
+    hit[perm[c]] = 1;
+    m[2 * (perm[c] * dim + c)] = 1.0;
+  }
+  return one_gate(state, n_qubits, targets, k, m.data(), nullptr);
+}
+
+int qsim_apply_superop(void* vec_rho, int n_qubits, const int* targets, int k, const double* superop,
+                       void* scratch, void*) {
+  if (!vec_rho || !targets || !superop) return qs::fail(QSIM_ERR_ARG, "qsim_apply_superop: null argument");
+  if (k < 1 || 2 * k > 10) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_superop: k must be in [1, 5]");
+  std::vector<int> t(2 * k);
+  for (int i = 0; i < k; ++i) { t[i] = targets[i]; t[k + i] = targets[i] + n_qubits; }
+  return one_gate(vec_rho, 2 * n_qubits, t.data(), 2 * k, superop, scratch);
+}
+
+int qsim_init_product(void* state, int n_qubits, const double* amps, void*) {
+  if (!state || !amps || n_qubits < 1 || n_qubits > 40) return qs::fail(QSIM_ERR_ARG, "qsim_init_product: bad argument");
+  qs_c128* s = (qs_c128*)state;
+  for (uint64_t i = 0; i < (1ull << n_qubits); ++i) s[i] = qs_product_amp(amps, n_qubits, i);
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int qsim_measure_probs(const void* state, int n_qubits, int qubit, const double* bra0, const double* bra1,
+                       double* out_norm2, void*) {
+  if (!state || !bra0 || !bra1 || !out_norm2) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: null argument");
+  if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: qubit out of range");
+  const qs_c128* s = (const qs_c128*)state;
+  const int pos = n_qubits - 1 - qubit;
+  double p0 = 0.0, p1 = 0.0;
+  for (uint64_t r = 0; r < (1ull << (n_qubits - 1)); ++r) {
+    const qs_c128 u = qs_contract(s, pos, r, bra0), v = qs_contract(s, pos, r, bra1);
+    p0 += u.x * u.x + u.y * u.y;
+    p1 += v.x * v.x + v.y * v.y;
+  }
+  out_norm2[0] = p0;
+  out_norm2[1] = p1;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_collapse(const void* in, void* out, int n_qubits, int qubit, const double* bra, double norm, void*) {
+  if (!in || !out || !bra) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: null argument");
+  if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: qubit out of range");
+  const int pos = n_qubits - 1 - qubit;
+  qs_c128* o = (qs_c128*)out;
+  for (uint64_t r = 0; r < (1ull << (n_qubits - 1)); ++r) {
+    qs_c128 v = qs_contract((const qs_c128*)in, pos, r, bra);
+    v.x /= norm; v.y /= norm;
+    o[r] = v;
+  }
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int qsim_insert(const void* in, void* out, int n_qubits, int position, const double* amp, void*) {
+  if (!in || !out || !amp) return qs::fail(QSIM_ERR_ARG, "qsim_insert: null argument");
+  if (n_qubits < 0 || position < 0 || position > n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_insert: position out of range");
+  qs_c128* o = (qs_c128*)out;
+  for (uint64_t i = 0; i < (1ull << (n_qubits + 1)); ++i)
+    o[i] = qs_insert_amp((const qs_c128*)in, n_qubits - position, i, amp);
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int qsim_reduce_norm2(const void* state, uint64_t n_amps, double* out, void*) {
+  if (!state || !out) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_norm2: null argument");
+  const qs_c128* s = (const qs_c128*)state;
+  double acc = 0.0;
+  for (uint64_t i = 0; i < n_amps; ++i) acc += s[i].x * s[i].x + s[i].y * s[i].y;
+  *out = acc;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_reduce_inner(const void* a, const void* b, uint64_t n_amps, double* out_re_im, void*) {
+  if (!a || !b || !out_re_im) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_inner: null argument");
+  const qs_c128 *u = (const qs_c128*)a, *v = (const qs_c128*)b;
+  double re = 0.0, im = 0.0;
+  for (uint64_t i = 0; i < n_amps; ++i) {
+    re += u[i].x * v[i].x + u[i].y * v[i].y;
+    im += u[i].x * v[i].y - u[i].y * v[i].x;
+  }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_reduce_expect(const void* ket, const void* rho, int n_qubits, double* out_re_im, void*) {
+  if (!ket || !rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_expect: bad argument");
+  const qs_c128 *k = (const qs_c128*)ket, *r = (const qs_c128*)rho;
+  const uint64_t dim = 1ull << n_qubits;
+  double re = 0.0, im = 0.0;
+  for (uint64_t i = 0; i < dim; ++i)
+    for (uint64_t j = 0; j < dim; ++j) {
+      const qs_c128 t = qs_cmul(r[i * dim + j], k[j]);
+      re += k[i].x * t.x + k[i].y * t.y;
+      im += k[i].x * t.y - k[i].y * t.x;
+    }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_reduce_purity(const void* rho, int n_qubits, double* out_re_im, void*) {
+  if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_purity: bad argument");
+  const qs_c128* r = (const qs_c128*)rho;
+  const uint64_t dim = 1ull << n_qubits;
+  double re = 0.0, im = 0.0;
+  for (uint64_t i = 0; i < dim; ++i)
+    for (uint64_t j = 0; j < dim; ++j) {
+      const qs_c128 t = qs_cmul(r[i * dim + j], r[j * dim + i]);
+      re += t.x;
+      im += t.y;
+    }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void*) {
+  if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_trace: bad argument");
+  const qs_c128* r = (const qs_c128*)rho;
+  const uint64_t dim = 1ull << n_qubits;
+  double re = 0.0, im = 0.0;
+  for (uint64_t i = 0; i < dim; ++i) { re += r[i * dim + i].x; im += r[i * dim + i].y; }
+  out_re_im[0] = re;
+  out_re_im[1] = im;
+  g_launches += 2;
+  return QSIM_OK;
+}
+
+int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets, int n_opcodes,
+                  const double* superops, const double* unitaries, const double* rho0, const double* psi0,
+                  double* out_fidelity, double* out_purity, double* out_rho, void*) {
+  if (!opcodes || !offsets || !superops || !unitaries || !rho0 || !psi0 || !out_fidelity || !out_purity)
+    return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: null argument");
+  if (nq < 1 || nq > 2) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_rb_batch: nq must be 1 or 2");
+  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 256) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
+  for (int64_t b = 0; b < n_seq; ++b) {
+    const int64_t lo = offsets[b], hi = offsets[b + 1];
+    if (nq == 2)
+      qs_rb_sequence<4>(opcodes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fidelity + b,
+                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 256 : nullptr);
+    else
+      qs_rb_sequence<2>(opcodes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fidelity + b,
+                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 16 : nullptr);
+  }
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, void*) {
+  if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
+  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
+    return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
+  const int pos = n_local - 1 - local_qubit;
+  const qs_c128* s = (const qs_c128*)shard;
+  qs_c128* b = (qs_c128*)sendbuf;
+  for (uint64_t r = 0; r < (1ull << (n_local - 1)); ++r) b[r] = s[qs_insert_bit(r, pos, (uint64_t)(1 - keep_bit))];
+  ++g_launches;
+  return QSIM_OK;
+}
+
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, void*) {
+  if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
+  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
+    return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
+  const int pos = n_local - 1 - local_qubit;
+  qs_c128* s = (qs_c128*)shard;
+  const qs_c128* b = (const qs_c128*)recvbuf;
+  for (uint64_t r = 0; r < (1ull << (n_local - 1)); ++r) s[qs_insert_bit(r, pos, (uint64_t)(1 - keep_bit))] = b[r];
+  ++g_launches;
+  return QSIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// sm_100a kernels and the device-facing half of the C ABI (include/qsim_b200.h).
+//
+// Everything here is memory-bound complex128 work: 16-byte (128-bit) loads and
+// stores per amplitude, shared-memory staging of 2^T-amplitude tiles so several
+// gates apply per HBM pass, persistent grids sized to the SM count.  No tensor
+// cores: tcgen05 has no f64 kind and the 2x2/4x4 updates have no GEMM shape.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "elem_ops.h"
+#include "planner.h"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+struct DevCtx {
+  bool ready = false;
+  int sms = 0;
+  double* d_partials = nullptr;   // [kReduceBlocks][2]
+  double* d_out = nullptr;        // [2]
+  double* h_out = nullptr;        // pinned [2]
+  int occ3 = 0, occ4 = 0;         // resident CTAs/SM of k_tile_pass<3>/<4> at the last smem size
+  int occ_smem = -1;
+};
+
+constexpr int kMaxDevices = 16;
+constexpr int kReduceThreads = 256;
+constexpr int kReduceBlocks = 148 * 8;
+DevCtx g_ctx[kMaxDevices];
+
+#define QS_CUDA(call)                                                                  \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return qs::fail(QSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+int bind_device(const void* ptr, DevCtx** ctx) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return qs::fail(QSIM_ERR_CUDA, std::string("cudaPointerGetAttributes: ") + cudaGetErrorString(e));
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+    return qs::fail(QSIM_ERR_ARG, "buffer is not device memory (no CPU path exists in this library)");
+  if (at.device < 0 || at.device >= kMaxDevices) return qs::fail(QSIM_ERR_ARG, "device index out of range");
+  QS_CUDA(cudaSetDevice(at.device));
+  DevCtx& c = g_ctx[at.device];
+  if (!c.ready) {
+    cudaDeviceProp prop;
+    QS_CUDA(cudaGetDeviceProperties(&prop, at.device));
+    c.sms = prop.multiProcessorCount;
+    QS_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks));
+    QS_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 2));
+    QS_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 2));
+    c.ready = true;
+  }
+  *ctx = &c;
+  return QSIM_OK;
+}
+
+// =====================================================================================
+// Tile pass: the fused multi-gate kernel (plan.h / tile_exec.h)
+// =====================================================================================
+template <int MAXR>
+__global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
+k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
+  extern __shared__ __align__(16) unsigned char qs_smem[];
+  qs_c128* tile = reinterpret_cast<qs_c128*>(qs_smem);
+  __shared__ uint32_t s_zmask[QS_MAX_STEPS];
+  __shared__ uint32_t s_gsign[QS_MAX_STEPS];
+  const uint32_t tid = threadIdx.x;
+  const int nsteps = (int)P.nsteps;
+
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint64_t base = qs_tile_base(P, t);
+    if ((int)tid < nsteps) qs_sign_prepare(P, (int)tid, base, &s_zmask[tid], &s_gsign[tid]);
+    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2);
+    __syncthreads();
+    for (int s = 0; s + 1 < nsteps; ++s) {
+      qs_phase_step_any<MAXR>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_gsign[s]);
+      __syncthreads();
+    }
+    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, s_zmask[nsteps - 1], s_gsign[nsteps - 1]);
+    __syncthreads();
+  }
+}
+
+int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
+  if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
+  const uint64_t ntiles = 1ull << (n - (int)P.T);
+  const int smem = (int)(sizeof(qs_c128) << P.T);
+  int maxr = 1;
+  for (uint32_t s = 0; s < P.nsteps; ++s) maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
+  if (ctx->occ_smem != smem) {
+    QS_CUDA(cudaFuncSetAttribute(k_tile_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    QS_CUDA(cudaFuncSetAttribute(k_tile_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ3, k_tile_pass<3>, QS_THREADS, smem));
+    QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ4, k_tile_pass<4>, QS_THREADS, smem));
+    ctx->occ_smem = smem;
+  }
+  const int occ = maxr <= 3 ? ctx->occ3 : ctx->occ4;
+  if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
+  uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
+  if (grid > ntiles) grid = ntiles;
+  if (maxr <= 3)
+    k_tile_pass<3><<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
+  else
+    k_tile_pass<4><<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+// =====================================================================================
+// Simple streaming kernels
+// =====================================================================================
+__global__ void k_init_product(qs_c128* state, int n, const double* __restrict__ amps, uint64_t count) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    state[i] = qs_product_amp(amps, n, i);
+}
+
+struct BraPair { double b[4]; };
+
+__global__ void k_collapse(const qs_c128* __restrict__ in, qs_c128* __restrict__ out, int pos,
+                           BraPair bra, double norm, uint64_t count) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    qs_c128 v = qs_contract(in, pos, r, bra.b);
+    v.x /= norm; v.y /= norm;
+    out[r] = v;
+  }
+}
+
+__global__ void k_insert(const qs_c128* __restrict__ in, qs_c128* __restrict__ out, int pos,
+                         BraPair amp, uint64_t count) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = qs_insert_amp(in, pos, i, amp.b);
+}
+
+struct BitList { int bits[10]; };
+
+__global__ void k_generic(const qs_c128* __restrict__ in, qs_c128* __restrict__ out,
+                          const double* __restrict__ mat, BitList bl, int k, uint64_t count) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = qs_generic_amp(in, mat, bl.bits, k, i);
+}
+
+__global__ void k_swap_pack(const qs_c128* __restrict__ shard, qs_c128* __restrict__ buf, int pos,
+                            uint64_t bit, uint64_t count) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
+       r += (uint64_t)gridDim.x * blockDim.x)
+    buf[r] = shard[qs_insert_bit(r, pos, bit)];
+}
+
+__global__ void k_swap_unpack(qs_c128* __restrict__ shard, const qs_c128* __restrict__ buf, int pos,
+                              uint64_t bit, uint64_t count) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
+       r += (uint64_t)gridDim.x * blockDim.x)
+    shard[qs_insert_bit(r, pos, bit)] = buf[r];
+}
+
+unsigned stream_grid(const DevCtx* ctx, uint64_t count, int threads) {
+  uint64_t blocks = (count + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)ctx->sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// =====================================================================================
+// Reductions: fixed grid, fixed tree -> bit-reproducible results run to run
+// =====================================================================================
+struct FnNorm2 {
+  const qs_c128* a;
+  __device__ void operator()(uint64_t i, double& s0, double& s1) const {
+    const qs_c128 v = a[i];
+    s0 += v.x * v.x + v.y * v.y;
+  }
+};
+struct FnInner {   // sum conj(a_i) b_i
+  const qs_c128 *a, *b;
+  __device__ void operator()(uint64_t i, double& s0, double& s1) const {
+    const qs_c128 u = a[i], v = b[i];
+    s0 += u.x * v.x + u.y * v.y;
+    s1 += u.x * v.y - u.y * v.x;
+  }
+};
+struct FnMeasure {  // s0 += |bra0 . pair|^2, s1 += |bra1 . pair|^2
+  const qs_c128* a;
+  int pos;
+  BraPair b0, b1;
+  __device__ void operator()(uint64_t r, double& s0, double& s1) const {
+    const qs_c128 u = qs_contract(a, pos, r, b0.b);
+    const qs_c128 v = qs_contract(a, pos, r, b1.b);
+    s0 += u.x * u.x + u.y * u.y;
+    s1 += v.x * v.x + v.y * v.y;
+  }
+};
+struct FnExpect {   // sum_ij conj(k_i) rho_ij k_j ; element e = i * dim + j
+  const qs_c128 *ket, *rho;
+  int n;
+  __device__ void operator()(uint64_t e, double& s0, double& s1) const {
+    const uint64_t i = e >> n, j = e & ((1ull << n) - 1ull);
+    const qs_c128 t = qs_cmul(rho[e], ket[j]);
+    const qs_c128 k = ket[i];
+    s0 += k.x * t.x + k.y * t.y;
+    s1 += k.x * t.y - k.y * t.x;
+  }
+};
+struct FnPurity {   // sum_ij rho_ij rho_ji
+  const qs_c128* rho;
+  int n;
+  __device__ void operator()(uint64_t e, double& s0, double& s1) const {
+    const uint64_t i = e >> n, j = e & ((1ull << n) - 1ull);
+    const qs_c128 t = qs_cmul(rho[e], rho[(j << n) | i]);
+    s0 += t.x;
+    s1 += t.y;
+  }
+};
+struct FnTrace {
+  const qs_c128* rho;
+  int n;
+  __device__ void operator()(uint64_t i, double& s0, double& s1) const {
+    const qs_c128 v = rho[(i << n) | i];
+    s0 += v.x;
+    s1 += v.y;
+  }
+};
+
+__device__ __forceinline__ void block_reduce2(double& s0, double& s1) {
+  __shared__ double w0[kReduceThreads / 32], w1[kReduceThreads / 32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, off);
+    s1 += __shfl_down_sync(0xffffffffu, s1, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { w0[warp] = s0; w1[warp] = s1; }
+  __syncthreads();
+  if (warp == 0) {
+    s0 = lane < kReduceThreads / 32 ? w0[lane] : 0.0;
+    s1 = lane < kReduceThreads / 32 ? w1[lane] : 0.0;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      s0 += __shfl_down_sync(0xffffffffu, s0, off);
+      s1 += __shfl_down_sync(0xffffffffu, s1, off);
+    }
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads) k_reduce(F f, uint64_t count, double* partials) {
+  double s0 = 0.0, s1 = 0.0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    f(i, s0, s1);
+  block_reduce2(s0, s1);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s0; partials[2 * blockIdx.x + 1] = s1; }
+}
+
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_final(const double* partials, int nblocks, double* out) {
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { s0 += partials[2 * i]; s1 += partials[2 * i + 1]; }
+  block_reduce2(s0, s1);
+  if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+}
+
+template <class F>
+int reduce_to_host(DevCtx* ctx, F f, uint64_t count, double* out2, cudaStream_t stream) {
+  uint64_t blocks = (count + kReduceThreads - 1) / kReduceThreads;
+  if (blocks > (uint64_t)kReduceBlocks) blocks = kReduceBlocks;
+  if (blocks < 1) blocks = 1;
+  k_reduce<F><<<(unsigned)blocks, kReduceThreads, 0, stream>>>(f, count, ctx->d_partials);
+  k_reduce_final<<<1, kReduceThreads, 0, stream>>>(ctx->d_partials, (int)blocks, ctx->d_out);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  QS_CUDA(cudaMemcpyAsync(ctx->h_out, ctx->d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  QS_CUDA(cudaStreamSynchronize(stream));
+  out2[0] = ctx->h_out[0];
+  out2[1] = ctx->h_out[1];
+  return QSIM_OK;
+}
+
+// =====================================================================================
+// Batched tiny-circuit executor
+// =====================================================================================
+template <int DIM>
+__global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint8_t* __restrict__ codes,
+                                                  const int64_t* __restrict__ offsets,
+                                                  const double* __restrict__ superops,
+                                                  const double* __restrict__ unitaries,
+                                                  const double* __restrict__ rho0,
+                                                  const double* __restrict__ psi0, double* out_fid,
+                                                  double* out_pur, double* out_rho) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= n_seq) return;
+  const int64_t lo = offsets[b], hi = offsets[b + 1];
+  qs_rb_sequence<DIM>(codes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fid + b, out_pur + b,
+                      out_rho ? out_rho + (size_t)b * 2 * DIM * DIM * DIM * DIM : nullptr);
+}
+
+int run_generic(DevCtx* ctx, const qs::Op& op, qs_c128* state, qs_c128* scratch, int n, cudaStream_t stream) {
+  if (!scratch) return qs::fail(QSIM_ERR_ARG, "a gate on more than 4 qubits needs a scratch buffer of 2^n amplitudes");
+  const int dim = 1 << op.k;
+  const size_t bytes = sizeof(double) * 2 * dim * dim;
+  std::vector<double> flat(2 * (size_t)dim * dim);
+  for (int e = 0; e < dim * dim; ++e) { flat[2 * e] = op.mat[e].real(); flat[2 * e + 1] = op.mat[e].imag(); }
+  double* d_mat = nullptr;
+  QS_CUDA(cudaMallocAsync(&d_mat, bytes, stream));
+  QS_CUDA(cudaMemcpyAsync(d_mat, flat.data(), bytes, cudaMemcpyHostToDevice, stream));
+  QS_CUDA(cudaStreamSynchronize(stream));     // flat goes out of scope; generic path is not the fast path
+  BitList bl;
+  for (int f = 0; f < op.k; ++f) bl.bits[f] = op.bits[f];
+  const uint64_t count = 1ull << n;
+  k_generic<<<stream_grid(ctx, count, 256), 256, 0, stream>>>(state, scratch, d_mat, bl, op.k, count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  QS_CUDA(cudaMemcpyAsync(state, scratch, sizeof(qs_c128) * count, cudaMemcpyDeviceToDevice, stream));
+  QS_CUDA(cudaFreeAsync(d_mat, stream));
+  return QSIM_OK;
+}
+
+int execute_plan(const qsim_plan* p, void* state, int n, void* scratch, void* stream) {
+  if (!p || !state) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: null argument");
+  if (n != p->n) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: plan was compiled for a different qubit count");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(state, &ctx);
+  if (rc != QSIM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (const qs::PlanItem& it : p->items) {
+    rc = it.generic ? run_generic(ctx, it.op, (qs_c128*)state, (qs_c128*)scratch, n, st)
+                    : launch_pass(ctx, it.pass, (qs_c128*)state, n, st);
+    if (rc != QSIM_OK) return rc;
+  }
+  return QSIM_OK;
+}
+
+int one_gate(void* state, int n, const int* targets, int k, const double* matrix, void* scratch, void* stream) {
+  qsim_circuit_t* c = nullptr;
+  int rc = qsim_circuit_create(n, &c);
+  if (rc != QSIM_OK) return rc;
+  rc = qsim_circuit_add_matrix(c, k, targets, matrix);
+  qsim_plan_t* p = nullptr;
+  if (rc == QSIM_OK) rc = qsim_plan_compile(c, nullptr, &p);
+  if (rc == QSIM_OK) rc = execute_plan(p, state, n, scratch, stream);
+  qsim_plan_destroy(p);
+  qsim_circuit_destroy(c);
+  return rc;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int qsim_has_cuda(void) { return 1; }
+
+int64_t qsim_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void* stream) {
+  return execute_plan(p, state, n_qubits, scratch, stream);
+}
+
+int qsim_apply_matrix(void* state, int n_qubits, const int* targets, int k, const double* matrix,
+                      void* scratch, void* stream) {
+  if (!state || !targets || !matrix) return qs::fail(QSIM_ERR_ARG, "qsim_apply_matrix: null argument");
+  return one_gate(state, n_qubits, targets, k, matrix, scratch, stream);
+}
+
+int qsim_apply_diagonal(void* state, int n_qubits, const int* targets, int k, const double* diag, void* stream) {
+  if (!state || !targets || !diag) return qs::fail(QSIM_ERR_ARG, "qsim_apply_diagonal: null argument");
+  if (k < 1 || k > QS_MAX_R) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_diagonal: k must be in [1, 4]");
+  const int dim = 1 << k;
+  std::vector<double> m(2 * (size_t)dim * dim, 0.0);
+  for (int d = 0; d < dim; ++d) { m[2 * (d * dim + d)] = diag[2 * d]; m[2 * (d * dim + d) + 1] = diag[2 * d + 1]; }
+  return one_gate(state, n_qubits, targets, k, m.data(), nullptr, stream);
+}
+
+int qsim_apply_permutation(void* state, int n_qubits, const int* targets, int k, const int* perm, void* stream) {
+  if (!state || !targets || !perm) return qs::fail(QSIM_ERR_ARG, "qsim_apply_permutation: null argument");
+  if (k < 1 || k > QS_MAX_R) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_permutation: k must be in [1, 4]");
+  const int dim = 1 << k;
+  std::vector<double> m(2 * (size_t)dim * dim, 0.0);
+  std::vector<char> hit(dim, 0);
+  for (int c = 0; c < dim; ++c) {
+    if (perm[c] < 0 || perm[c] >= dim || hit[perm[c]]) return qs::fail(QSIM_ERR_ARG, "qsim_apply_permutation: not a permutation");
+    hit[perm[c]] = 1;
+    m[2 * (perm[c] * dim + c)] = 1.0;
+  }
+  return one_gate(state, n_qubits, targets, k, m.data(), nullptr, stream);
+}
+
+int qsim_apply_superop(void* vec_rho, int n_qubits, const int* targets, int k, const double* superop,
+                       void* scratch, void* stream) {
+  if (!vec_rho || !targets || !superop) return qs::fail(QSIM_ERR_ARG, "qsim_apply_superop: null argument");
+  if (k < 1 || 2 * k > 10) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_apply_superop: k must be in [1, 5]");
+  std::vector<int> t(2 * k);
+  for (int i = 0; i < k; ++i) { t[i] = targets[i]; t[k + i] = targets[i] + n_qubits; }
+  return one_gate(vec_rho, 2 * n_qubits, t.data(), 2 * k, superop, scratch, stream);
+}
+
+int qsim_init_product(void* state, int n_qubits, const double* amps, void* stream) {
+  if (!state || !amps || n_qubits < 1 || n_qubits > 40) return qs::fail(QSIM_ERR_ARG, "qsim_init_product: bad argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(state, &ctx);
+  if (rc != QSIM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d_amps = nullptr;
+  const size_t bytes = sizeof(double) * 4 * n_qubits;
+  QS_CUDA(cudaMallocAsync(&d_amps, bytes, st));
+  QS_CUDA(cudaMemcpyAsync(d_amps, amps, bytes, cudaMemcpyHostToDevice, st));
+  const uint64_t count = 1ull << n_qubits;
+  k_init_product<<<stream_grid(ctx, count, 256), 256, 0, st>>>((qs_c128*)state, n_qubits, d_amps, count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  QS_CUDA(cudaFreeAsync(d_amps, st));
+  return QSIM_OK;
+}
+
+int qsim_measure_probs(const void* state, int n_qubits, int qubit, const double* bra0, const double* bra1,
+                       double* out_norm2, void* stream) {
+  if (!state || !bra0 || !bra1 || !out_norm2) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: null argument");
+  if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: qubit out of range");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(state, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnMeasure f;
+  f.a = (const qs_c128*)state;
+  f.pos = n_qubits - 1 - qubit;
+  memcpy(f.b0.b, bra0, sizeof(f.b0.b));
+  memcpy(f.b1.b, bra1, sizeof(f.b1.b));
+  return reduce_to_host(ctx, f, 1ull << (n_qubits - 1), out_norm2, (cudaStream_t)stream);
+}
+
+int qsim_collapse(const void* in, void* out, int n_qubits, int qubit, const double* bra, double norm, void* stream) {
+  if (!in || !out || !bra) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: null argument");
+  if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: qubit out of range");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(in, &ctx);
+  if (rc != QSIM_OK) return rc;
+  BraPair b;
+  memcpy(b.b, bra, sizeof(b.b));
+  const uint64_t count = 1ull << (n_qubits - 1);
+  k_collapse<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const qs_c128*)in, (qs_c128*)out, n_qubits - 1 - qubit, b, norm, count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+int qsim_insert(const void* in, void* out, int n_qubits, int position, const double* amp, void* stream) {
+  if (!in || !out || !amp) return qs::fail(QSIM_ERR_ARG, "qsim_insert: null argument");
+  if (n_qubits < 0 || position < 0 || position > n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_insert: position out of range");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(in, &ctx);
+  if (rc != QSIM_OK) return rc;
+  BraPair a;
+  memcpy(a.b, amp, sizeof(a.b));
+  const uint64_t count = 1ull << (n_qubits + 1);
+  // the new register has n+1 qubits; reference position p is index bit (n+1)-1-p
+  k_insert<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const qs_c128*)in, (qs_c128*)out, n_qubits - position, a, count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+int qsim_reduce_norm2(const void* state, uint64_t n_amps, double* out, void* stream) {
+  if (!state || !out) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_norm2: null argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(state, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnNorm2 f{(const qs_c128*)state};
+  double r[2];
+  rc = reduce_to_host(ctx, f, n_amps, r, (cudaStream_t)stream);
+  if (rc == QSIM_OK) *out = r[0];
+  return rc;
+}
+
+int qsim_reduce_inner(const void* a, const void* b, uint64_t n_amps, double* out_re_im, void* stream) {
+  if (!a || !b || !out_re_im) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_inner: null argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(a, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnInner f{(const qs_c128*)a, (const qs_c128*)b};
+  return reduce_to_host(ctx, f, n_amps, out_re_im, (cudaStream_t)stream);
+}
+
+int qsim_reduce_expect(const void* ket, const void* rho, int n_qubits, double* out_re_im, void* stream) {
+  if (!ket || !rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_expect: bad argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(rho, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnExpect f{(const qs_c128*)ket, (const qs_c128*)rho, n_qubits};
+  return reduce_to_host(ctx, f, 1ull << (2 * n_qubits), out_re_im, (cudaStream_t)stream);
+}
+
+int qsim_reduce_purity(const void* rho, int n_qubits, double* out_re_im, void* stream) {
+  if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_purity: bad argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(rho, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnPurity f{(const qs_c128*)rho, n_qubits};
+  return reduce_to_host(ctx, f, 1ull << (2 * n_qubits), out_re_im, (cudaStream_t)stream);
+}
+
+int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void* stream) {
+  if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_trace: bad argument");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(rho, &ctx);
+  if (rc != QSIM_OK) return rc;
+  FnTrace f{(const qs_c128*)rho, n_qubits};
+  return reduce_to_host(ctx, f, 1ull << n_qubits, out_re_im, (cudaStream_t)stream);
+}
+
+int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets, int n_opcodes,
+                  const double* superops, const double* unitaries, const double* rho0, const double* psi0,
+                  double* out_fidelity, double* out_purity, double* out_rho, void* stream) {
+  if (!opcodes || !offsets || !superops || !unitaries || !rho0 || !psi0 || !out_fidelity || !out_purity)
+    return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: null argument");
+  if (nq < 1 || nq > 2) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_rb_batch: nq must be 1 or 2");
+  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 256) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
+  if (n_seq == 0) return QSIM_OK;
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(out_fidelity, &ctx);
+  if (rc != QSIM_OK) return rc;
+  const unsigned blocks = (unsigned)((n_seq + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nq == 2)
+    k_rb_batch<4><<<blocks, 128, 0, st>>>(n_seq, opcodes, offsets, superops, unitaries, rho0, psi0,
+                                         out_fidelity, out_purity, out_rho);
+  else
+    k_rb_batch<2><<<blocks, 128, 0, st>>>(n_seq, opcodes, offsets, superops, unitaries, rho0, psi0,
+                                         out_fidelity, out_purity, out_rho);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, void* stream) {
+  if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
+  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
+    return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(shard, &ctx);
+  if (rc != QSIM_OK) return rc;
+  const uint64_t count = 1ull << (n_local - 1);
+  k_swap_pack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const qs_c128*)shard, (qs_c128*)sendbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, void* stream) {
+  if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
+  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
+    return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
+  DevCtx* ctx = nullptr;
+  int rc = bind_device(shard, &ctx);
+  if (rc != QSIM_OK) return rc;
+  const uint64_t count = 1ull << (n_local - 1);
+  k_swap_unpack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
+      (qs_c128*)shard, (const qs_c128*)recvbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), count);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+}  // extern "C"

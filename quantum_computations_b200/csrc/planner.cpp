@@ -1,0 +1,484 @@
+// Circuit container, single-qubit merging and the greedy fusion planner.
+//
+// Replaces the per-gate Python loop of the reference executor
+// (DV/simulator.py:40-52): instead of one full-state operation per gate, gates
+// are packed into *passes* (plan.h).  Three facts do the work:
+//   * runs of single-qubit gates on one qubit collapse into one 2x2 matrix, and
+//     diagonal ones slide through CZ/Z gates to reach a neighbour to merge with;
+//   * CZ/Z are signs that depend only on index bits, so they cost no memory
+//     traffic and may involve qubits outside the tile;
+//   * non-diagonal gates need their qubits inside the tile, so each pass picks
+//     the T tile bits that let it absorb the most pending gates.
+#include "planner.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace qs {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+const char* last_error() { return g_error.c_str(); }
+
+qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
+  qsim_plan_options_t o{};
+  if (opt) o = *opt;
+  if (o.tile_bits <= 0) o.tile_bits = 12;
+  if (o.low_bits <= 0) o.low_bits = 4;
+  if (o.max_group <= 0) o.max_group = 3;
+  if (o.max_dense_ops <= 0) o.max_dense_ops = 16;
+  if (o.lookahead <= 0) o.lookahead = 600;
+  if (o.merge_1q <= 0) o.merge_1q = 1;
+  if (o.tile_bits > QS_MAX_T) o.tile_bits = QS_MAX_T;
+  if (o.max_group > QS_MAX_R) o.max_group = QS_MAX_R;
+  if (o.low_bits + QS_MAX_R > o.tile_bits) o.low_bits = o.tile_bits - QS_MAX_R;
+  if (o.low_bits < 0) o.low_bits = 0;
+  return o;
+}
+
+// ---- small dense helpers -------------------------------------------------------
+
+static bool is_diagonal(const std::vector<cplx>& m, int dim) {
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c)
+      if (r != c && (m[r * dim + c].real() != 0.0 || m[r * dim + c].imag() != 0.0)) return false;
+  return true;
+}
+
+static bool is_exact(const cplx& v, double re) { return v.real() == re && v.imag() == 0.0; }
+
+static bool is_cz(const std::vector<cplx>& m) {
+  if (!is_diagonal(m, 4)) return false;
+  return is_exact(m[0], 1.0) && is_exact(m[5], 1.0) && is_exact(m[10], 1.0) && is_exact(m[15], -1.0);
+}
+
+static bool is_z(const std::vector<cplx>& m) {
+  return is_diagonal(m, 2) && is_exact(m[0], 1.0) && is_exact(m[3], -1.0);
+}
+
+static bool is_identity(const std::vector<cplx>& m, int dim) {
+  if (!is_diagonal(m, dim)) return false;
+  for (int r = 0; r < dim; ++r)
+    if (!is_exact(m[r * dim + r], 1.0)) return false;
+  return true;
+}
+
+// 2x2 product a*b
+static std::vector<cplx> mul2(const std::vector<cplx>& a, const std::vector<cplx>& b) {
+  std::vector<cplx> o(4);
+  o[0] = a[0] * b[0] + a[1] * b[2];
+  o[1] = a[0] * b[1] + a[1] * b[3];
+  o[2] = a[2] * b[0] + a[3] * b[2];
+  o[3] = a[2] * b[1] + a[3] * b[3];
+  return o;
+}
+
+// (g on factor f) * m   -- g applied AFTER m
+static void fold_left(Op& op, int f, const std::vector<cplx>& g) {
+  const int k = op.k, dim = 1 << k, bit = 1 << (k - 1 - f);
+  std::vector<cplx> o(op.mat.size());
+  for (int r = 0; r < dim; ++r) {
+    const int rf = (r & bit) ? 1 : 0;
+    const int r0 = r & ~bit, r1 = r | bit;
+    for (int c = 0; c < dim; ++c)
+      o[r * dim + c] = g[rf * 2 + 0] * op.mat[r0 * dim + c] + g[rf * 2 + 1] * op.mat[r1 * dim + c];
+  }
+  op.mat.swap(o);
+  op.diag = is_diagonal(op.mat, dim);
+}
+
+// m * (g on factor f)   -- g applied BEFORE m
+static void fold_right(Op& op, int f, const std::vector<cplx>& g) {
+  const int k = op.k, dim = 1 << k, bit = 1 << (k - 1 - f);
+  std::vector<cplx> o(op.mat.size());
+  for (int r = 0; r < dim; ++r)
+    for (int c = 0; c < dim; ++c) {
+      const int cf = (c & bit) ? 1 : 0;
+      const int c0 = c & ~bit, c1 = c | bit;
+      o[r * dim + c] = op.mat[r * dim + c0] * g[0 * 2 + cf] + op.mat[r * dim + c1] * g[1 * 2 + cf];
+    }
+  op.mat.swap(o);
+  op.diag = is_diagonal(op.mat, dim);
+}
+
+// ---- single-qubit merging ---------------------------------------------------------
+
+namespace {
+enum Since { SINCE_NOTHING = 0, SINCE_DIAG = 1, SINCE_BLOCKED = 2 };
+struct BitTrack {
+  bool has_pending = false;
+  std::vector<cplx> pending;   // product of not-yet-emitted 1q gates on this bit
+  bool pending_diag = true;
+  int last_op = -1;            // output op a later 1q gate may still fold into
+  int last_factor = 0;
+  int since = SINCE_BLOCKED;   // what has been emitted on this bit after last_op
+};
+}  // namespace
+
+std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
+  std::vector<Op> out;
+  out.reserve(in.size());
+  std::vector<BitTrack> tr(n);
+
+  auto emit_pending = [&](int b) {
+    BitTrack& t = tr[b];
+    if (!t.has_pending) return;
+    t.has_pending = false;
+    if (is_identity(t.pending, 2)) return;
+    Op o;
+    if (is_z(t.pending)) {
+      o.kind = OP_SIGN;
+      o.k = 2;
+      o.bits = {b, b};
+      o.diag = true;
+      out.push_back(o);
+      if (t.since == SINCE_NOTHING) t.since = SINCE_DIAG;
+      return;
+    }
+    o.kind = OP_DENSE;
+    o.k = 1;
+    o.bits = {b};
+    o.mat = t.pending;
+    o.diag = t.pending_diag;
+    out.push_back(o);
+    t.last_op = (int)out.size() - 1;
+    t.last_factor = 0;
+    t.since = SINCE_NOTHING;
+  };
+
+  for (const Op& g : in) {
+    if (g.kind == OP_DENSE && g.k == 1) {
+      const int b = g.bits[0];
+      BitTrack& t = tr[b];
+      if (t.has_pending) {
+        t.pending = mul2(g.mat, t.pending);
+        t.pending_diag = is_diagonal(t.pending, 2);
+      } else if (t.last_op >= 0 && (t.since == SINCE_NOTHING || (g.diag && t.since == SINCE_DIAG))) {
+        fold_left(out[t.last_op], t.last_factor, g.mat);
+      } else {
+        t.has_pending = true;
+        t.pending = g.mat;
+        t.pending_diag = g.diag;
+      }
+      continue;
+    }
+    if (g.kind == OP_SIGN) {
+      for (int b : g.bits) {
+        BitTrack& t = tr[b];
+        if (t.has_pending && !t.pending_diag) emit_pending(b);   // diagonal pendings slide through
+        if (t.since == SINCE_NOTHING) t.since = SINCE_DIAG;
+      }
+      out.push_back(g);
+      continue;
+    }
+    // multi-qubit dense gate: swallow pending single-qubit gates on its qubits
+    Op d = g;
+    for (int f = 0; f < d.k; ++f) {
+      BitTrack& t = tr[d.bits[f]];
+      if (t.has_pending) {
+        fold_right(d, f, t.pending);
+        t.has_pending = false;
+      }
+    }
+    out.push_back(d);
+    const int idx = (int)out.size() - 1;
+    for (int f = 0; f < d.k; ++f) {
+      BitTrack& t = tr[d.bits[f]];
+      if (d.diag) {
+        // a later diagonal 1q gate commutes with d and may still reach last_op
+        if (t.since == SINCE_NOTHING) t.since = SINCE_DIAG;
+        if (t.last_op < 0) { t.last_op = idx; t.last_factor = f; t.since = SINCE_NOTHING; }
+      } else {
+        t.last_op = idx;
+        t.last_factor = f;
+        t.since = SINCE_NOTHING;
+      }
+    }
+  }
+  for (int b = 0; b < n; ++b) emit_pending(b);
+  return out;
+}
+
+// ---- greedy pass construction --------------------------------------------------------
+
+namespace {
+
+struct Walker {
+  int n;
+  const std::vector<Op>& ops;
+  const std::vector<uint64_t>& masks;
+  std::vector<char>& done;
+  qsim_plan_options_t opt;
+
+  // Walk the pending ops in order and take every op that can run in a pass whose
+  // tile is the bit set S.  With `pass` == nullptr only the score is computed
+  // (and at most opt.lookahead pending ops are visited).
+  // Returns dense_taken * 4096 + min(sign_taken, 4095).
+  long walk(size_t first, uint64_t S, QsPass* pass, std::vector<size_t>* taken_idx) const {
+    const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    uint64_t blocked_full = 0, blocked_diag = 0;
+    int dense_taken = 0, sign_taken = 0, visited = 0;
+
+    int lpos[64];
+    {
+      int t = 0;
+      for (int b = 0; b < n; ++b) lpos[b] = (S >> b & 1) ? t++ : -1;
+    }
+
+    int nsteps = 0, ncoef = 0, npairs = 0;
+    int cur_step = -1, cur_r = 0;            // open 1Q step that may still take members
+    uint64_t cur_mask = 0;
+    uint8_t pend[256][2];                    // sign pairs waiting for the next step
+    int npend = 0;
+
+    auto flush_pairs_into = [&](QsStep* st) {
+      if (st) {
+        uint8_t* dst = pass->pairs + 2 * npairs;
+        int w = 0, n_oo = 0, n_lo = 0, n_ll = 0;
+        for (int p = 0; p < npend; ++p) {        // both bits outside the tile
+          const int a = pend[p][0], b = pend[p][1];
+          if (lpos[a] < 0 && lpos[b] < 0) { dst[w++] = (uint8_t)a; dst[w++] = (uint8_t)b; ++n_oo; }
+        }
+        for (int p = 0; p < npend; ++p) {        // one inside: (local position, outer bit)
+          const int a = pend[p][0], b = pend[p][1];
+          if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
+            const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
+            dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
+          }
+        }
+        for (int p = 0; p < npend; ++p) {        // both inside
+          const int a = pend[p][0], b = pend[p][1];
+          if (lpos[a] >= 0 && lpos[b] >= 0) {
+            dst[w++] = (uint8_t)lpos[a]; dst[w++] = (uint8_t)lpos[b]; ++n_ll;
+          }
+        }
+        st->pair_off = (uint16_t)npairs;
+        st->n_oo = (uint8_t)n_oo; st->n_lo = (uint8_t)n_lo; st->n_ll = (uint8_t)n_ll;
+      }
+      npairs += npend;
+      npend = 0;
+    };
+
+    const int max_steps = QS_MAX_STEPS - 1;   // the last slot is the final sign step
+    for (size_t i = first; i < ops.size(); ++i) {
+      if (done[i]) continue;
+      if (!pass && ++visited > opt.lookahead) break;
+      const Op& op = ops[i];
+      const uint64_t m = masks[i];
+      if (op.kind == OP_SIGN) {
+        const bool room = npairs + npend + 1 <= QS_MAX_PAIRS && npend < 250;
+        if ((m & blocked_full) == 0 && room) {
+          // CZ is an involution: a repeated pair cancels
+          const int a = std::min(op.bits[0], op.bits[1]), b = std::max(op.bits[0], op.bits[1]);
+          int hit = -1;
+          for (int p = 0; p < npend; ++p)
+            if (pend[p][0] == a && pend[p][1] == b) { hit = p; break; }
+          if (hit >= 0) {
+            pend[hit][0] = pend[npend - 1][0]; pend[hit][1] = pend[npend - 1][1];
+            --npend;
+          } else {
+            pend[npend][0] = (uint8_t)a; pend[npend][1] = (uint8_t)b;
+            ++npend;
+          }
+          ++sign_taken;
+          if (taken_idx) taken_idx->push_back(i);
+        } else {
+          blocked_diag |= m;
+        }
+      } else {
+        const bool in_tile = (m & ~S) == 0;
+        const bool free_bits = (m & blocked_full) == 0 && (op.diag || (m & blocked_diag) == 0);
+        bool take = in_tile && free_bits && op.k <= QS_MAX_R && dense_taken < opt.max_dense_ops;
+        bool join = false;
+        if (take) {
+          join = op.k == 1 && cur_step >= 0 && npend == 0 && cur_r < opt.max_group &&
+                 !(cur_mask & m);
+          if (!join) {
+            const int need = (op.k == 1) ? 8 * opt.max_group : 2 * (1 << op.k) * (1 << op.k);
+            if (nsteps >= max_steps || ncoef + need > QS_MAX_COEF) take = false;
+          }
+        }
+        if (take && join) {
+          if (pass) {
+            QsStep& st = pass->steps[cur_step];
+            st.gpos[st.r] = (uint8_t)lpos[op.bits[0]];
+            double* dst = pass->coef + st.coef_off + 8 * st.r;
+            for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+            st.r++;
+          }
+          cur_r++;
+          cur_mask |= m;
+        } else if (take) {
+          QsStep* st = pass ? &pass->steps[nsteps] : nullptr;
+          if (st) *st = QsStep{};
+          flush_pairs_into(st);
+          const int dim = 1 << op.k;
+          if (st) {
+            st->coef_off = (uint16_t)ncoef;
+            st->kind = (op.k == 1) ? QS_STEP_1Q : QS_STEP_DENSE;
+            st->r = (uint8_t)op.k;
+            for (int f = 0; f < op.k; ++f) st->gpos[f] = (uint8_t)lpos[op.bits[f]];
+            double* dst = pass->coef + ncoef;
+            for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+          }
+          if (op.k == 1) {
+            ncoef += 8 * opt.max_group;       // room for later members of the group
+            cur_step = nsteps; cur_r = 1; cur_mask = m;
+          } else {
+            ncoef += 2 * dim * dim;
+            cur_step = -1; cur_r = 0; cur_mask = 0;
+          }
+          ++nsteps;
+        }
+        if (take) {
+          ++dense_taken;
+          if (taken_idx) taken_idx->push_back(i);
+        } else if (op.diag) {
+          blocked_diag |= m;
+        } else {
+          blocked_full |= m;
+        }
+      }
+      if ((blocked_full & all) == all) break;
+    }
+
+    if (pass) {
+      QsStep& fin = pass->steps[nsteps];
+      fin = QsStep{};
+      fin.kind = QS_STEP_SIGN;
+      flush_pairs_into(&fin);
+      ++nsteps;
+      pass->nsteps = (uint32_t)nsteps;
+      pass->ncoef = (uint32_t)ncoef;
+      pass->npairs = (uint32_t)npairs;
+    }
+    return (long)dense_taken * 4096 + std::min(sign_taken, 4095);
+  }
+};
+
+// Order the free local positions of a step: the three fastest thread bits go to
+// positions that differ mod 3 (conflict-free with the XOR-fold swizzle), the
+// rest ascending.
+void order_free_positions(QsStep& st, int T) {
+  bool used[QS_MAX_T + 1] = {false};
+  for (int f = 0; f < st.r; ++f) used[st.gpos[f]] = true;
+  std::vector<int> freep;
+  for (int p = 0; p < T; ++p)
+    if (!used[p]) freep.push_back(p);
+  std::vector<int> first3;
+  bool have[3] = {false, false, false};
+  for (int p : freep)
+    if (!have[p % 3]) { have[p % 3] = true; first3.push_back(p); }
+  std::vector<int> order = first3;
+  // pad the leading triple from the remaining positions if a residue is missing
+  for (int p : freep)
+    if (std::find(order.begin(), order.end(), p) == order.end()) order.push_back(p);
+  if (first3.size() < 3) {
+    // keep deterministic: leading entries are first3 then ascending rest (already so)
+  }
+  for (size_t i = 0; i < order.size() && i < QS_MAX_T; ++i) st.fpos[i] = (uint8_t)order[i];
+}
+
+}  // namespace
+
+int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt, qsim_plan* out) {
+  out->n = n;
+  out->items.clear();
+  qsim_plan_stats_t& stats = out->stats;
+  stats.n_merged_ops = (int64_t)ops.size();
+  std::vector<char> done(ops.size(), 0);
+  std::vector<uint64_t> masks(ops.size());
+  for (size_t i = 0; i < ops.size(); ++i) masks[i] = ops[i].mask();
+  Walker wk{n, ops, masks, done, opt};
+  const int T = std::min(opt.tile_bits, n);
+  const int L = std::min(opt.low_bits, T);
+
+  // first pending dense op per bit (tie-break when growing the tile)
+  size_t first = 0;
+  while (true) {
+    while (first < ops.size() && done[first]) ++first;
+    if (first >= ops.size()) break;
+
+    const Op& head = ops[first];
+    if (head.kind == OP_DENSE && head.k > QS_MAX_R) {
+      PlanItem it;
+      it.generic = true;
+      it.op = head;
+      out->items.push_back(std::move(it));
+      done[first] = 1;
+      stats.n_generic++;
+      continue;
+    }
+
+    uint64_t S = 0;
+    if (n <= T) {
+      S = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    } else {
+      S = (1ull << L) - 1ull;
+      if (head.kind == OP_DENSE) S |= head.mask();
+      int size = __builtin_popcountll(S);
+      // distance (in pending ops) to the next dense gate on each bit: tie-break
+      std::vector<int> next_dense(n, 1 << 30);
+      {
+        int seen = 0;
+        for (size_t i = first; i < ops.size() && seen < opt.lookahead; ++i) {
+          if (done[i]) continue;
+          ++seen;
+          if (ops[i].kind != OP_DENSE) continue;
+          for (int b : ops[i].bits)
+            if (next_dense[b] == (1 << 30)) next_dense[b] = seen;
+        }
+      }
+      while (size < T) {
+        long best_score = -1;
+        int best_bit = -1;
+        for (int b = 0; b < n; ++b) {
+          if (S >> b & 1) continue;
+          const long sc = wk.walk(first, S | (1ull << b), nullptr, nullptr);
+          if (sc > best_score ||
+              (sc == best_score && best_bit >= 0 && next_dense[b] < next_dense[best_bit])) {
+            best_score = sc;
+            best_bit = b;
+          }
+        }
+        S |= 1ull << best_bit;
+        ++size;
+      }
+    }
+
+    PlanItem it;
+    it.generic = false;
+    QsPass& P = it.pass;
+    memset(&P, 0, sizeof(P));
+    P.T = (uint32_t)__builtin_popcountll(S);
+    {
+      int l = 0;
+      for (int b = 0; b < n; ++b)
+        if (S >> b & 1) P.tile_bits[l++] = (uint8_t)b;
+    }
+    std::vector<size_t> taken;
+    wk.walk(first, S, &P, &taken);
+    if (taken.empty())
+      return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
+    for (size_t idx : taken) done[idx] = 1;
+    for (uint32_t s = 0; s < P.nsteps; ++s) {
+      QsStep& st = P.steps[s];
+      order_free_positions(st, (int)P.T);
+      if (st.kind != QS_STEP_SIGN) {
+        stats.n_steps++;
+        stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
+      }
+      stats.n_sign += st.n_oo + st.n_lo + st.n_ll;
+    }
+    stats.n_passes++;
+    out->items.push_back(std::move(it));
+  }
+  return QSIM_OK;
+}
+
+}  // namespace qs

@@ -1,0 +1,65 @@
+// Host-side circuit container and fusion planner (no CUDA dependency, so the
+// same sources also build into the host emulator used by the CPU tests).
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qsim_b200.h"
+#include "plan.h"
+
+namespace qs {
+
+typedef std::complex<double> cplx;
+
+enum OpKind { OP_DENSE = 0, OP_SIGN = 1 };
+
+// One gate in library coordinates: bits[f] is the index bit that matrix factor
+// f (f = 0 most significant) acts on.
+struct Op {
+  int kind = OP_DENSE;
+  int k = 0;
+  std::vector<int> bits;
+  bool diag = false;
+  std::vector<cplx> mat;     // 2^k x 2^k row-major (empty for OP_SIGN)
+  uint64_t mask() const {
+    uint64_t m = 0;
+    for (int b : bits) m |= 1ull << b;
+    return m;
+  }
+};
+
+struct PlanItem {
+  bool generic = false;
+  QsPass pass;               // valid when !generic
+  Op op;                     // valid when generic
+};
+
+}  // namespace qs
+
+struct qsim_circuit {
+  int n = 0;
+  std::vector<qs::Op> ops;
+};
+
+struct qsim_plan {
+  int n = 0;
+  std::vector<qs::PlanItem> items;
+  qsim_plan_stats_t stats{};
+};
+
+namespace qs {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+// Single-qubit merging pre-pass (returns the reduced op list).
+std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in);
+
+// Greedy tile/pass construction.
+int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt, qsim_plan* out);
+
+qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt);
+
+}  // namespace qs

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def emu_backend():
+    from emu_backend import emu
+    return emu()
+
+
+@pytest.fixture(scope="session")
+def cuda_backend():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from quantum_computations_b200 import engine
+    return engine.get_backend()
