@@ -48,8 +48,10 @@ def measure(state: np.ndarray, qubit: int, theta: float, phi: float,
     n = qubit_count(state)
     v0, v1 = measurement_vectors(theta, phi)
     t = state.reshape((2,) * n)
-    r0 = np.tensordot(v0, t, axes=([0], [qubit])).reshape(-1)
-    r1 = np.tensordot(v1, t, axes=([0], [qubit])).reshape(-1)
+    # a 1-qubit register collapses to a 0-d array in the reference (vector @ vector)
+    shape = () if n == 1 else (-1,)
+    r0 = np.tensordot(v0, t, axes=([0], [qubit])).reshape(shape)
+    r1 = np.tensordot(v1, t, axes=([0], [qubit])).reshape(shape)
     n0 = np.linalg.norm(r0)
     n1 = np.linalg.norm(r1)
     if forced is not None:

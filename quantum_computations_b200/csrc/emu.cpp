@@ -259,10 +259,10 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* 
     const int64_t lo = offsets[b], hi = offsets[b + 1];
     if (nq == 2)
       qs_rb_sequence<4>(opcodes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fidelity + b,
-                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 256 : nullptr);
+                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 16 : nullptr);
     else
       qs_rb_sequence<2>(opcodes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fidelity + b,
-                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 16 : nullptr);
+                        out_purity + b, out_rho ? out_rho + (size_t)b * 2 * 4 : nullptr);
   }
   ++g_launches;
   return QSIM_OK;

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint8_t* 
   if (b >= n_seq) return;
   const int64_t lo = offsets[b], hi = offsets[b + 1];
   qs_rb_sequence<DIM>(codes + lo, hi - lo, superops, unitaries, rho0, psi0, out_fid + b, out_pur + b,
-                      out_rho ? out_rho + (size_t)b * 2 * DIM * DIM * DIM * DIM : nullptr);
+                      out_rho ? out_rho + (size_t)b * 2 * DIM * DIM : nullptr);
 }
 
 int run_generic(DevCtx* ctx, const qs::Op& op, qs_c128* state, qs_c128* scratch, int n, cudaStream_t stream) {

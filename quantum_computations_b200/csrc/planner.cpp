@@ -231,8 +231,13 @@ struct Walker {
     }
 
     int nsteps = 0, ncoef = 0, npairs = 0;
-    int cur_step = -1, cur_r = 0;            // open 1Q step that may still take members
-    uint64_t cur_mask = 0;
+    // Earliest-fit packing of single-qubit gates into 1Q steps: a gate on bit c may
+    // join any existing step after the last matrix on c and not before the step
+    // whose sign block holds the last CZ/Z on c (it commutes with everything else).
+    int step_r[QS_MAX_STEPS];                // members of a 1Q step; -1 = dense step (closed)
+    int last_dense[64], last_sign[64];
+    for (int b = 0; b < 64; ++b) { last_dense[b] = -1; last_sign[b] = 0; }
+    uint64_t pend_mask = 0;                  // bits touched by the pending sign pairs
     uint8_t pend[256][2];                    // sign pairs waiting for the next step
     int npend = 0;
 
@@ -262,6 +267,9 @@ struct Walker {
       }
       npairs += npend;
       npend = 0;
+      for (int b = 0; b < n; ++b)
+        if (pend_mask >> b & 1) last_sign[b] = nsteps;    // nsteps = index of the receiving step
+      pend_mask = 0;
     };
 
     const int max_steps = QS_MAX_STEPS - 1;   // the last slot is the final sign step
@@ -285,6 +293,7 @@ struct Walker {
             pend[npend][0] = (uint8_t)a; pend[npend][1] = (uint8_t)b;
             ++npend;
           }
+          pend_mask |= m;
           ++sign_taken;
           if (taken_idx) taken_idx->push_back(i);
         } else {
@@ -294,25 +303,29 @@ struct Walker {
         const bool in_tile = (m & ~S) == 0;
         const bool free_bits = (m & blocked_full) == 0 && (op.diag || (m & blocked_diag) == 0);
         bool take = in_tile && free_bits && op.k <= QS_MAX_R && dense_taken < opt.max_dense_ops;
-        bool join = false;
+        int join = -1;
         if (take) {
-          join = op.k == 1 && cur_step >= 0 && npend == 0 && cur_r < opt.max_group &&
-                 !(cur_mask & m);
-          if (!join) {
+          if (op.k == 1 && !(pend_mask & m)) {
+            const int c = op.bits[0];
+            const int earliest = std::max(last_dense[c] + 1, last_sign[c]);
+            for (int sidx = earliest; sidx < nsteps; ++sidx)
+              if (step_r[sidx] >= 1 && step_r[sidx] < opt.max_group) { join = sidx; break; }
+          }
+          if (join < 0) {
             const int need = (op.k == 1) ? 8 * opt.max_group : 2 * (1 << op.k) * (1 << op.k);
             if (nsteps >= max_steps || ncoef + need > QS_MAX_COEF) take = false;
           }
         }
-        if (take && join) {
+        if (take && join >= 0) {
           if (pass) {
-            QsStep& st = pass->steps[cur_step];
+            QsStep& st = pass->steps[join];
             st.gpos[st.r] = (uint8_t)lpos[op.bits[0]];
             double* dst = pass->coef + st.coef_off + 8 * st.r;
             for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
             st.r++;
           }
-          cur_r++;
-          cur_mask |= m;
+          step_r[join]++;
+          last_dense[op.bits[0]] = join;
         } else if (take) {
           QsStep* st = pass ? &pass->steps[nsteps] : nullptr;
           if (st) *st = QsStep{};
@@ -328,11 +341,12 @@ struct Walker {
           }
           if (op.k == 1) {
             ncoef += 8 * opt.max_group;       // room for later members of the group
-            cur_step = nsteps; cur_r = 1; cur_mask = m;
+            step_r[nsteps] = 1;
           } else {
             ncoef += 2 * dim * dim;
-            cur_step = -1; cur_r = 0; cur_mask = 0;
+            step_r[nsteps] = -1;
           }
+          for (int b : op.bits) last_dense[b] = nsteps;
           ++nsteps;
         }
         if (take) {

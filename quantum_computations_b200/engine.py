@@ -180,6 +180,9 @@ class DeviceState:
         self.ndim = int(ndim)
         # dtype the reference would have produced so far (NumPy promotion)
         self.host_dtype = np.dtype(host_dtype)
+        # measuring the last qubit of a ket leaves a 0-d array in the reference
+        # (vector @ vector, DV/gates.py:176); remembered so to_numpy() can mirror it
+        self.scalar_shape = False
 
     # -- construction ------------------------------------------------------------------
     @classmethod
@@ -220,6 +223,8 @@ class DeviceState:
     @property
     def shape(self):
         if self.ndim == 1:
+            if self.scalar_shape and self.n_bits == 0:
+                return ()
             return (1 << self.n_bits,)
         d = 1 << (self.n_bits // 2)
         return (d, d)
@@ -346,7 +351,9 @@ def measure(state: DeviceState, qubit: int, vec0: np.ndarray, vec1: np.ndarray, 
     bra = (b0, b1)[s]
     _capi.check(lib, lib.qsim_collapse(be.ptr(state.buf), be.ptr(out), n, int(qubit),
                                        _dptr(bra.view(np.float64)), float((norm0, norm1)[s]), be.stream()))
-    return DeviceState(be, out, n - 1, 1, np.complex128), s
+    collapsed = DeviceState(be, out, n - 1, 1, np.complex128)
+    collapsed.scalar_shape = (n == 1)
+    return collapsed, s
 
 
 def _measure_dm(state: DeviceState, qubit: int, vec0, vec1, forced):

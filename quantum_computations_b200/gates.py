@@ -65,6 +65,11 @@ class Gate:
         self.indices = renamed
 
     # -- engine hooks -----------------------------------------------------------------
+    @property
+    def _fusable(self) -> bool:
+        """True if ``Simulator.run`` may batch this gate into a fused plan."""
+        return self.matrix is not None
+
     def lowered(self, num_qubits: int, is_density: bool):
         """``[(targets, matrix), ...]`` in buffer-qubit numbering.  A density
         matrix lives on the device as its row-major vec, where U rho U^dagger is

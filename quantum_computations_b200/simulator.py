@@ -53,7 +53,7 @@ def _is_fusable(gate) -> bool:
     """Plain matrix gates whose ``apply`` is the stock one can be batched into a
     fused plan; anything else (M, Insert, user subclasses overriding ``apply``)
     is applied on its own."""
-    return isinstance(gate, Gate) and type(gate).apply is Gate.apply and gate.matrix is not None
+    return isinstance(gate, Gate) and type(gate).apply is Gate.apply and gate._fusable
 
 
 class Simulator:

@@ -1,0 +1,300 @@
+"""Parity checks shared by the CPU (host-emulator backend) and GPU (CUDA backend)
+test modules.  Every function takes the backend to run the package on and
+compares with the golden vectors produced by the real reference
+(tests/golden/make_golden.py) and/or with the CPU oracle.
+
+Tolerance: the north star asks for <= 1e-10 relative in complex128; the checks
+use RTOL = 1e-12 on max|diff| / max|ref| unless stated otherwise.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from golden.specs import as_oracle_ops, from_spec
+from oracle import dense_ref, gkp_noise, strided
+from quantum_computations_b200 import channels, engine, gates, simulator, states, workloads
+from quantum_computations_b200 import numpy_quantum as npq
+from quantum_computations_b200.batched import BatchedSimulator
+from quantum_computations_b200.simulator import Simulator
+from quantum_computations_b200.states import State
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-12
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return json.loads(str(z["meta"])), z
+
+
+def rel_err(got, ref) -> float:
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = max(float(np.abs(ref).max()), 1e-300)
+    return float(np.abs(got - ref).max()) / scale
+
+
+def mk(spec, z):
+    return from_spec(spec, gates, simulator, z, channels, states)
+
+
+def dev(arr, backend):
+    return engine.DeviceState.from_numpy(arr, backend)
+
+
+# ---- single gates ------------------------------------------------------------------------
+def check_single_gates(backend):
+    meta, z = load("single_gates.npz")
+    worst = 0.0
+    for rec in meta:
+        gate = mk(rec["gate"], z)
+        got = gate.apply(dev(z[rec["in"]], backend)).to_numpy()
+        ref = z[rec["out"]]
+        worst = max(worst, rel_err(got, ref))
+        if "dtype" in rec:
+            assert str(got.dtype) == rec["dtype"], (rec, got.dtype)
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_density_gates(backend):
+    meta, z = load("density_gates.npz")
+    worst = 0.0
+    for rec in meta:
+        got = mk(rec["gate"], z).apply(dev(z[rec["in"]], backend)).to_numpy()
+        worst = max(worst, rel_err(got, z[rec["out"]]))
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_measure(backend):
+    meta, z = load("measure.npz")
+    worst = 0.0
+    for rec in meta:
+        if "stream" in rec:
+            psi = z[rec["in"]]
+            np.random.seed(rec["seed"])
+            d = dev(psi, backend)
+            got = [int(gates.MZ(rec["q"]).apply(d)[1]) for _ in range(len(rec["stream"]))]
+            assert got == rec["stream"]          # bit-exact outcome stream
+            continue
+        m = gates.M(rec["q"], rec["theta"], rec["phi"], result=rec["forced"])
+        if rec["seed"] is not None:
+            np.random.seed(rec["seed"])
+        out, s = m.apply(dev(z[rec["in"]], backend))
+        assert s == rec["s"], rec
+        worst = max(worst, rel_err(out.to_numpy(), z[rec["out"]]))
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_insert(backend):
+    meta, z = load("insert.npz")
+    worst = 0.0
+    for rec in meta:
+        out = gates.Insert(rec["pos"], State[rec["state"]]).apply(dev(z[rec["in"]], backend))
+        ref = z[rec["out"]]
+        got = out.to_numpy()
+        worst = max(worst, rel_err(got, ref))
+        assert got.dtype == ref.dtype, (rec, got.dtype, ref.dtype)
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_kraus(backend):
+    meta, z = load("kraus.npz")
+    worst = 0.0
+    for rec in meta:
+        ch = channels.Channel(rec["indices"], list(z[rec["kraus"]]))
+        got = ch.apply(dev(z[rec["in"]], backend)).to_numpy()
+        worst = max(worst, rel_err(got, z[rec["out"]]))
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_metrics(backend):
+    meta, z = load("metrics.npz")
+    for rec in meta:
+        n = rec["n"]
+        a, b, ra, rb = (z[f"{k}{n}"] for k in ("a", "b", "ra", "rb"))
+        da, db_, dra, drb = (dev(x, backend) for x in (a, b, ra, rb))
+        assert abs(npq.fidelity(da, db_) - rec["f_kk"]) < 1e-12
+        assert abs(npq.fidelity(da, drb) - rec["f_kr"]) < 1e-12
+        assert abs(npq.fidelity(dra, db_) - rec["f_rk"]) < 1e-12
+        assert abs(npq.fidelity(dra, drb) - rec["f_rr"]) < 1e-9     # eigvals branch (host LAPACK)
+        assert abs(npq.fidelity(a, drb) - rec["f_kr"]) < 1e-12       # mixed host/device operands
+        assert abs(npq.purity(dra) - rec["purity"]) < 1e-12
+        assert abs(npq.norm(dev(3.0 * a, backend)) - rec["norm"]) < 1e-12
+
+
+# ---- circuits ---------------------------------------------------------------------------------
+def check_sv_circuits(backend, plan_options=None, max_n=13):
+    meta, z = load("circuits.npz")
+    worst = 0.0
+    for rec in meta:
+        if rec["n"] > max_n:
+            continue
+        circ = workloads.sv_random_circuit(rec["n"], rec["depth"], rec["seed"])
+        assert len(circ) == rec["ngates"]
+        got = Simulator(circ, backend=backend, plan_options=plan_options).run([State.ZERO] * rec["n"])
+        worst = max(worst, rel_err(got, z[rec["out"]]))
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_grover(backend):
+    meta, z = load("grover.npz")
+    worst = 0.0
+    for rec in meta:
+        circ = [mk(s, z) for s in rec["circuit"]]
+        init = None if rec["kind"] == "full" else [State[s] for s in rec["init"]]
+        got = Simulator(circ, backend=backend).run(init)
+        ref = z[rec["out"]]
+        worst = max(worst, rel_err(got, ref))
+        probs = np.abs(got) ** 2
+        for t in rec["tagged"]:                       # ideal Grover: 1/2 on each tagged state
+            assert abs(probs[t] - 0.5) < 1e-12
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_noisy_grover(backend):
+    meta, z = load("noisy_grover.npz")
+    worst = 0.0
+    for rec in meta:
+        circ = [mk(s, z) for s in rec["circuit"]]
+        noise = channels.GKPNoise(rec["db"])
+        psi0 = npq.tensor(*(State[s].get() for s in rec["init"])).astype(np.complex128)
+        rho0 = npq.ket2dm(psi0)
+        got = Simulator(noise.noisy(circ), backend=backend).run(rho0)
+        worst = max(worst, rel_err(got, z[rec["out"]]))
+        success = sum(got[t, t].real for t in rec["tagged"])
+        assert abs(success - rec["success"]) < 1e-12
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_sim_measure(backend):
+    meta, z = load("sim_measure.npz")
+    circ = [mk(s, z) for s in meta["circuit"]]
+    worst = 0.0
+    for run in meta["runs"]:
+        np.random.seed(run["seed"])
+        sim = Simulator(circ, backend=backend)
+        got = sim.run(None)
+        assert sim.results == run["results"], (sim.results, run["results"])
+        worst = max(worst, rel_err(got, z[run["out"]]))
+    assert worst < RTOL, worst
+    return worst
+
+
+def check_rb(backend):
+    """Circuit generator equality, ideal kets vs the reference, and the batched
+    noisy executor vs the oracle's density-matrix path."""
+    meta, z = load("rb.npz")
+    rng = np.random.default_rng(meta["seed"])
+    circuits = []
+    for i, rec in enumerate(meta["samples"]):
+        circ = workloads.rb_random_circuit(2, rec["depth"], rng)
+        want = [mk(s, z) for s in rec["circuit"]]
+        assert [repr(g) for g in circ] == [repr(g) for g in want], i     # same draws, same circuit
+        got = Simulator(circ, backend=backend).run([State.ZERO] * 2)
+        assert rel_err(got, z[rec["out"]]) < RTOL
+        circuits.append(circ)
+    db = 10.0
+    noise = channels.GKPNoise(db)
+    res = BatchedSimulator(2, noise, backend=backend).run(circuits, return_rho=True)
+    for i, circ in enumerate(circuits):
+        rho = np.zeros((4, 4), dtype=np.complex128)
+        rho[0, 0] = 1.0
+        for gate in circ:
+            rho = dense_ref.apply_matrix(rho, gate.indices, gate.matrix)
+            for q, (px, pz) in zip(gate.indices, noise.flips_for(gate)):
+                rho = dense_ref.apply_kraus(rho, [q], gkp_noise.pauli_flip_kraus(px, pz))
+        ideal = z[meta["samples"][i]["out"]]
+        assert rel_err(res["rho"][i], rho) < RTOL
+        assert abs(res["fidelity"][i] - dense_ref.fidelity(rho, ideal)) < 1e-12
+        assert abs(res["purity"][i] - dense_ref.purity(rho)) < 1e-12
+    # noise-free batch reproduces fidelity 1, purity 1
+    clean = BatchedSimulator(2, None, backend=backend).run(circuits)
+    assert np.allclose(clean["fidelity"], 1.0, atol=1e-12) and np.allclose(clean["purity"], 1.0, atol=1e-12)
+
+
+# ---- randomised differential test against the oracle ------------------------------------------------
+def random_circuit(n, length, rng):
+    circ = []
+    for _ in range(length):
+        r = int(rng.integers(0, 13))
+        q = int(rng.integers(0, n))
+        others = [x for x in range(n) if x != q]
+        q2 = int(rng.choice(others)) if others else None
+        if r == 0 or q2 is None and r >= 4 and r not in (7, 8, 9):
+            circ.append(gates.H(q))
+        elif r == 1:
+            circ.append(gates.T(q))
+        elif r == 2:
+            circ.append(gates.X(q))
+        elif r == 3:
+            circ.append(gates.RZ(q, float(rng.uniform(0, 2 * np.pi))))
+        elif r == 4:
+            circ.append(gates.CZ(q, q2))
+        elif r == 5:
+            circ.append(gates.CX(q, q2))
+        elif r == 6:
+            circ.append(gates.SWAP(q, q2))
+        elif r == 7:
+            circ.append(gates.Z(q))
+        elif r == 8:
+            circ.append(gates.Y(q))
+        elif r == 9:
+            circ.append(gates.P(q))
+        elif r == 10:
+            m = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+            circ.append(gates.Gate([q, q2], m / 2))
+        elif r == 11:
+            rest = [x for x in others if x != q2]
+            if rest:
+                q3 = int(rng.choice(rest))
+                m = rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8))
+                circ.append(gates.Gate([q2, q, q3], m / 3))
+        else:
+            d = np.exp(1j * rng.uniform(0, 2 * np.pi, size=4))
+            circ.append(gates.Gate([q, q2], np.diag(d)))
+    return circ
+
+
+def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for _ in range(trials):
+        n = int(rng.integers(n_range[0], n_range[1] + 1))
+        opts = dict(tile_bits=int(rng.integers(tile_range[0], tile_range[1] + 1)),
+                    low_bits=int(rng.integers(0, 5)), max_group=int(rng.integers(1, 5)),
+                    max_dense_ops=int(rng.integers(1, 24)), merge_1q=int(rng.integers(1, 3)))
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        psi /= np.linalg.norm(psi)
+        circ = random_circuit(n, int(rng.integers(1, 80)), rng)
+        got = Simulator(circ, backend=backend, plan_options=opts).run(psi)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        err = rel_err(got, ref)
+        assert err < RTOL, (n, opts, err)
+        worst = max(worst, err)
+    return worst
+
+
+def check_dm_layers_vs_oracle(backend, n, depth, seed, db=10.0):
+    """Config C3 at small N: noisy layered Clifford+T circuit on a density matrix."""
+    noise = channels.GKPNoise(db)
+    layers = workloads.dm_random_layers(n, depth, seed)
+    circ = noise.noisy([g for layer in layers for g in layer])
+    rho0 = np.zeros((2 ** n, 2 ** n), dtype=np.complex128)
+    rho0[0, 0] = 1.0
+    got = Simulator(circ, backend=backend).run(rho0)
+    ref, _ = strided.run(as_oracle_ops(circ), rho0)
+    err = rel_err(got, ref)
+    assert err < RTOL, err
+    assert abs(np.trace(got).real - 1.0) < 1e-12
+    return err

@@ -1,0 +1,114 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libqsim_b200.so)
+against the golden vectors of the real reference and the CPU oracle.  Same
+checks as tests/test_emulator_parity.py, plus sizes only a GPU can hold, where
+parity is established through size-independent properties."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from golden.specs import as_oracle_ops
+from oracle import strided
+from quantum_computations_b200 import engine, gates, workloads
+from quantum_computations_b200.simulator import Simulator
+from quantum_computations_b200.states import State
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_cuda(cuda_backend):
+    assert cuda_backend.lib.qsim_has_cuda() == 1
+    before = engine.launch_count(cuda_backend)
+    gates.H(0).apply(np.array([1.0, 0.0]))
+    assert engine.launch_count(cuda_backend) > before
+
+
+def test_single_gates(cuda_backend):
+    pc.check_single_gates(cuda_backend)
+
+
+def test_density_gates(cuda_backend):
+    pc.check_density_gates(cuda_backend)
+
+
+def test_measure(cuda_backend):
+    pc.check_measure(cuda_backend)
+
+
+def test_insert(cuda_backend):
+    pc.check_insert(cuda_backend)
+
+
+def test_kraus(cuda_backend):
+    pc.check_kraus(cuda_backend)
+
+
+def test_metrics(cuda_backend):
+    pc.check_metrics(cuda_backend)
+
+
+def test_sv_circuits(cuda_backend):
+    pc.check_sv_circuits(cuda_backend)
+    pc.check_sv_circuits(cuda_backend, plan_options=dict(tile_bits=7, low_bits=2, max_group=2))
+    pc.check_sv_circuits(cuda_backend, plan_options=dict(tile_bits=11, low_bits=5, max_group=1))
+
+
+def test_grover(cuda_backend):
+    pc.check_grover(cuda_backend)
+    pc.check_noisy_grover(cuda_backend)
+
+
+def test_sim_measure(cuda_backend):
+    pc.check_sim_measure(cuda_backend)
+
+
+def test_rb(cuda_backend):
+    pc.check_rb(cuda_backend)
+
+
+def test_random_vs_oracle_small_tiles(cuda_backend):
+    pc.check_random_vs_oracle(cuda_backend, trials=60, n_range=(1, 12), tile_range=(5, 9), seed=21)
+
+
+def test_random_vs_oracle_default_tiles(cuda_backend):
+    pc.check_random_vs_oracle(cuda_backend, trials=12, n_range=(12, 18), tile_range=(10, 13), seed=22)
+
+
+def test_dm_layers(cuda_backend):
+    pc.check_dm_layers_vs_oracle(cuda_backend, n=4, depth=6, seed=12)
+    pc.check_dm_layers_vs_oracle(cuda_backend, n=6, depth=4, seed=12)
+    pc.check_dm_layers_vs_oracle(cuda_backend, n=8, depth=2, seed=12)
+
+
+def test_sv_22q_vs_oracle(cuda_backend):
+    """Config C4's generator at a size the strided oracle still finishes in seconds."""
+    n, depth = 22, 3
+    circ = workloads.sv_random_circuit(n, depth, 30)
+    got = Simulator(circ, backend=cuda_backend).run([State.ZERO] * n)
+    psi0 = np.zeros(2 ** n, dtype=np.complex128)
+    psi0[0] = 1.0
+    ref, _ = strided.run(as_oracle_ops(circ), psi0)
+    assert pc.rel_err(got, ref) < pc.RTOL
+
+
+@pytest.mark.parametrize("n", [26, 30])
+def test_circuit_then_inverse_returns_zero_state(cuda_backend, n):
+    """No oracle reaches this size: U^-1 U |0> must be |0> and the norm must not
+    drift."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < (16 << n) * 1.2:
+        pytest.skip("not enough device memory")
+    depth = 6
+    circ = workloads.sv_random_circuit(n, depth, 30)
+    both = circ + workloads.inverse_circuit(circ)
+    mid = Simulator(circ, backend=cuda_backend).run([State.ZERO] * n, return_device=True)
+    assert abs(mid.norm() - 1.0) < 1e-12
+    # probability mass must have left |0...0> before the inverse brings it back
+    amp0 = mid.buf[0].item()
+    assert abs(amp0) < 0.9
+    del mid
+    out = Simulator(both, backend=cuda_backend).run([State.ZERO] * n, return_device=True)
+    assert abs(out.norm() - 1.0) < 1e-12
+    assert abs(out.buf[0].item() - 1.0) < 1e-10
+    rest = torch.linalg.vector_norm(out.buf[1:]).item()
+    assert rest < 1e-10
