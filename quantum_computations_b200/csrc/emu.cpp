@@ -23,16 +23,24 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   std::vector<qs_c128> tile((size_t)1 << P.T);
   std::vector<uint32_t> zmask(P.nsteps), gsign(P.nsteps);
   const int nsteps = (int)P.nsteps;
+  bool dense = false;
+  for (int s = 0; s < nsteps; ++s) dense |= P.steps[s].kind == QS_STEP_DENSE;
+  uint64_t ghi[1 << (QS_MAX_T - QS_THREADS_LOG2)];
+  for (uint32_t i = 0; i < (1u << (QS_MAX_T - QS_THREADS_LOG2)); ++i) ghi[i] = qs_global_hi(P, i, QS_THREADS_LOG2);
   for (uint64_t t = 0; t < ntiles; ++t) {
     const uint64_t base = qs_tile_base(P, t);
     for (int s = 0; s < nsteps; ++s) qs_sign_prepare(P, s, base, &zmask[s], &gsign[s]);
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2);
+      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, qs_global_lo(P, tid, QS_THREADS_LOG2), ghi);
     for (int s = 0; s + 1 < nsteps; ++s)
-      for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-        qs_phase_step_any<4>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
+      for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
+        // same variant selection as launch_pass() in kernels.cu
+        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
+        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
+      }
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, zmask[nsteps - 1], gsign[nsteps - 1]);
+      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, qs_global_lo(P, tid, QS_THREADS_LOG2), ghi,
+                     zmask[nsteps - 1], gsign[nsteps - 1]);
   }
   ++g_launches;
 }

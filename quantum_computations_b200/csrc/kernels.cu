@@ -26,7 +26,7 @@ struct DevCtx {
   double* d_partials = nullptr;   // [kReduceBlocks][2]
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
-  int occ3 = 0, occ4 = 0;         // resident CTAs/SM of k_tile_pass<3>/<4> at the last smem size
+  int occ[4] = {0, 0, 0, 0};      // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
 
@@ -70,51 +70,64 @@ int bind_device(const void* ptr, DevCtx** ctx) {
 // =====================================================================================
 // Tile pass: the fused multi-gate kernel (plan.h / tile_exec.h)
 // =====================================================================================
-template <int MAXR>
+template <int MAXR, bool DENSE>
 __global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* tile = reinterpret_cast<qs_c128*>(qs_smem);
   __shared__ uint32_t s_zmask[QS_MAX_STEPS];
   __shared__ uint32_t s_gsign[QS_MAX_STEPS];
+  __shared__ uint64_t s_ghi[1 << (QS_MAX_T - QS_THREADS_LOG2)];
   const uint32_t tid = threadIdx.x;
   const int nsteps = (int)P.nsteps;
+
+  // tile-independent pieces of the global addresses
+  const uint64_t glo = qs_global_lo(P, tid, QS_THREADS_LOG2);
+  if (tid < (1u << (QS_MAX_T - QS_THREADS_LOG2))) s_ghi[tid] = qs_global_hi(P, tid, QS_THREADS_LOG2);
+  __syncthreads();
 
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t base = qs_tile_base(P, t);
     if ((int)tid < nsteps) qs_sign_prepare(P, (int)tid, base, &s_zmask[tid], &s_gsign[tid]);
-    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2);
+    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_ghi);
     __syncthreads();
     for (int s = 0; s + 1 < nsteps; ++s) {
-      qs_phase_step_any<MAXR>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_gsign[s]);
+      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_gsign[s]);
       __syncthreads();
     }
-    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, s_zmask[nsteps - 1], s_gsign[nsteps - 1]);
+    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_ghi, s_zmask[nsteps - 1],
+                   s_gsign[nsteps - 1]);
     __syncthreads();
   }
 }
+
+typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t);
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
   const uint64_t ntiles = 1ull << (n - (int)P.T);
   const int smem = (int)(sizeof(qs_c128) << P.T);
   int maxr = 1;
-  for (uint32_t s = 0; s < P.nsteps; ++s) maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
+  bool dense = false;
+  for (uint32_t s = 0; s < P.nsteps; ++s) {
+    maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
+    dense |= P.steps[s].kind == QS_STEP_DENSE;
+  }
+  static const TileKernel variants[4] = {k_tile_pass<3, false>, k_tile_pass<3, true>,
+                                         k_tile_pass<4, false>, k_tile_pass<4, true>};
+  const int vi = (maxr <= 3 ? 0 : 2) + (dense ? 1 : 0);
   if (ctx->occ_smem != smem) {
-    QS_CUDA(cudaFuncSetAttribute(k_tile_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    QS_CUDA(cudaFuncSetAttribute(k_tile_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ3, k_tile_pass<3>, QS_THREADS, smem));
-    QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ4, k_tile_pass<4>, QS_THREADS, smem));
+    for (int v = 0; v < 4; ++v) {
+      QS_CUDA(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], QS_THREADS, smem));
+    }
     ctx->occ_smem = smem;
   }
-  const int occ = maxr <= 3 ? ctx->occ3 : ctx->occ4;
+  const int occ = ctx->occ[vi];
   if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
   uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
   if (grid > ntiles) grid = ntiles;
-  if (maxr <= 3)
-    k_tile_pass<3><<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
-  else
-    k_tile_pass<4><<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -13,6 +13,15 @@
 // (a block of CZ/Z gates, which may involve ANY index bit), applies either r
 // independent 2x2 matrices or one dense 2^r x 2^r matrix, and stores back.
 //
+// Sign blocks.  A block of CZ/Z gates multiplies amplitude i by (-1)^q(i) with q
+// a quadratic form over GF(2) in the index bits.  Relative to a tile it splits
+//   q = g  +  z . j  +  Q(j)           (j = local index inside the tile)
+// into a tile-uniform bit g (pairs of outer bits), a linear part z (local Z
+// gates: `zconst`; CZ between a local and an outer bit: the `lo` pairs, resolved
+// per tile) and a quadratic part Q over local bits only, stored as symmetric
+// neighbour masks `nsym`.  The kernels evaluate it with a handful of popcounts
+// per work item instead of a loop over pairs per amplitude (tile_exec.h).
+//
 // Index-bit convention inside the library: bit b of the linear index.  The
 // reference numbers qubits from the most significant end, so reference qubit q
 // of an n-qubit register is bit n-1-q (DV/numpy_quantum.py:243-247).
@@ -22,8 +31,8 @@
 #define QS_MAX_T        13     // largest tile: 2^13 amplitudes = 128 KiB
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
 #define QS_MAX_STEPS    56
-#define QS_MAX_PAIRS    640    // sign pairs per pass (all steps together)
-#define QS_MAX_COEF     2944   // doubles of matrix coefficients per pass
+#define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
+#define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #define QS_THREADS_LOG2 8
 #define QS_THREADS      (1 << QS_THREADS_LOG2)
 
@@ -38,14 +47,14 @@ struct QsStep {
   uint8_t  r;                    // number of group bits (0 for QS_STEP_SIGN)
   uint8_t  gpos[QS_MAX_R];       // local position of matrix factor f (f=0: most significant)
   uint8_t  fpos[QS_MAX_T];       // the T-r free local positions, in thread-scatter order
-  uint8_t  pad0;
+  uint8_t  has_sign;             // 1 if the step's sign block is not empty
   uint16_t coef_off;             // first coefficient (in doubles) in QsPass::coef
   // sign block applied to the amplitudes as they are loaded for this step
   uint16_t pair_off;             // first pair (index into QsPass::pairs, 2 bytes each)
   uint8_t  n_oo;                 // pairs with both bits outside the tile (global bit numbers)
   uint8_t  n_lo;                 // pairs (local position, outer global bit)
-  uint8_t  n_ll;                 // pairs (local position, local position)
-  uint8_t  pad1;
+  uint16_t zconst;               // local positions carrying a Z
+  uint16_t nsym[QS_MAX_T];       // nsym[p]: local positions CZ-coupled to local position p
 };
 
 struct QsPass {

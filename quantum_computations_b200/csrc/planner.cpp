@@ -256,14 +256,22 @@ struct Walker {
             dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
           }
         }
-        for (int p = 0; p < npend; ++p) {        // both inside
+        for (int p = 0; p < npend; ++p) {        // both inside: neighbour masks / local Z
           const int a = pend[p][0], b = pend[p][1];
           if (lpos[a] >= 0 && lpos[b] >= 0) {
-            dst[w++] = (uint8_t)lpos[a]; dst[w++] = (uint8_t)lpos[b]; ++n_ll;
+            if (a == b) {
+              st->zconst ^= (uint16_t)(1u << lpos[a]);
+            } else {
+              st->nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
+              st->nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
+            }
+            ++n_ll;
           }
         }
         st->pair_off = (uint16_t)npairs;
-        st->n_oo = (uint8_t)n_oo; st->n_lo = (uint8_t)n_lo; st->n_ll = (uint8_t)n_ll;
+        st->n_oo = (uint8_t)n_oo; st->n_lo = (uint8_t)n_lo;
+        st->has_sign = (n_oo + n_lo + n_ll) > 0 ? 1 : 0;
+        (void)w;
       }
       npairs += npend;
       npend = 0;
@@ -487,7 +495,11 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
         stats.n_steps++;
         stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
       }
-      stats.n_sign += st.n_oo + st.n_lo + st.n_ll;
+      {
+        int ll = __builtin_popcount(st.zconst);
+        for (uint32_t p2 = 0; p2 < P.T; ++p2) ll += __builtin_popcount((uint32_t)st.nsym[p2] & ~((2u << p2) - 1u) & 0xffffu);
+        stats.n_sign += st.n_oo + st.n_lo + ll;
+      }
     }
     stats.n_passes++;
     out->items.push_back(std::move(it));

@@ -14,11 +14,11 @@
 
 struct qs_c128 { double x, y; };   // layout-compatible with double2 / complex128
 
-QS_HD int qs_popc(uint32_t v) {
+QS_HD uint32_t qs_par(uint32_t v) {
 #if defined(__CUDA_ARCH__)
-  return __popc(v);
+  return (uint32_t)__popc(v) & 1u;
 #else
-  return __builtin_popcount(v);
+  return (uint32_t)__builtin_popcount(v) & 1u;
 #endif
 }
 
@@ -58,12 +58,24 @@ QS_HD uint64_t qs_tile_base(const QsPass& P, uint64_t tile) {
   return base;
 }
 
-// Per tile and per step: the part of the step's sign block that is uniform over
-// the tile (gsign) or linear in the local index (zmask).
+// Global-index contribution of the thread id (local bits 0..nthr_log2-1) and of
+// the per-thread iteration counter i (the remaining local bits).  Both are the
+// same for every tile of a pass, so the kernel computes them once.
+QS_HD uint64_t qs_global_lo(const QsPass& P, uint32_t tid, uint32_t nthr_log2) {
+  const int lo_bits = (int)(P.T < nthr_log2 ? P.T : nthr_log2);
+  return qs_scatter64(tid, P.tile_bits, lo_bits);
+}
+QS_HD uint64_t qs_global_hi(const QsPass& P, uint32_t i, uint32_t nthr_log2) {
+  if (P.T <= nthr_log2) return 0;
+  return qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2));
+}
+
+// ---- sign blocks ------------------------------------------------------------------------
+// Per tile and per step: the tile-uniform bit g and the linear mask z (plan.h).
 QS_HD void qs_sign_prepare(const QsPass& P, int s, uint64_t base, uint32_t* zmask, uint32_t* gsign) {
   const QsStep& st = P.steps[s];
   const uint8_t* pr = P.pairs + 2 * (uint32_t)st.pair_off;
-  uint32_t g = 0, z = 0;
+  uint32_t g = 0, z = st.zconst;
   for (int i = 0; i < st.n_oo; ++i, pr += 2)
     g ^= (uint32_t)((base >> pr[0]) & (base >> pr[1]) & 1ull);
   for (int i = 0; i < st.n_lo; ++i, pr += 2)
@@ -72,46 +84,89 @@ QS_HD void qs_sign_prepare(const QsPass& P, int s, uint64_t base, uint32_t* zmas
   *gsign = g;
 }
 
-// Sign (0/1) of local index j under step s's block.
-QS_HD uint32_t qs_sign_of(const QsPass& P, const QsStep& st, uint32_t j, uint32_t zmask, uint32_t gsign) {
-  uint32_t sg = gsign ^ (uint32_t)(qs_popc(j & zmask) & 1);
-  const uint8_t* pr = P.pairs + 2 * ((uint32_t)st.pair_off + st.n_oo + st.n_lo);
-  for (int i = 0; i < st.n_ll; ++i, pr += 2) sg ^= (j >> pr[0]) & (j >> pr[1]) & 1u;
+// Q(x) for x = the scatter of the low `count` bits of v over pos[]: every coupled
+// pair inside x counted once (the partner with the higher position).
+QS_HD uint32_t qs_quad_scattered(const QsStep& st, uint32_t v, const uint8_t* pos, int count, uint32_t x) {
+  uint32_t q = 0;
+  for (int b = 0; b < count; ++b) {
+    const uint32_t p = pos[b];
+    const uint32_t up = ~((2u << p) - 1u);
+    q ^= ((v >> b) & 1u) & qs_par(x & st.nsym[p] & up);
+  }
+  return q;
+}
+
+// XOR of the neighbour masks of the set bits of the scattered value.
+QS_HD uint32_t qs_neigh_scattered(const QsStep& st, uint32_t v, const uint8_t* pos, int count) {
+  uint32_t m = 0;
+  for (int b = 0; b < count; ++b) m ^= (0u - ((v >> b) & 1u)) & st.nsym[pos[b]];
+  return m;
+}
+
+// Reference implementation of the whole sign (used by the host emulator's
+// self-check and by nothing on the hot path): g + z.j + Q(j).
+QS_HD uint32_t qs_sign_slow(const QsStep& st, uint32_t T, uint32_t j, uint32_t zmask, uint32_t gsign) {
+  uint32_t sg = gsign ^ qs_par(j & zmask);
+  for (uint32_t p = 0; p < T; ++p)
+    if ((j >> p) & 1u) sg ^= qs_par(j & st.nsym[p] & ~((2u << p) - 1u));
   return sg;
 }
 
+QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
+  // sign_bit is 0 or 0x80000000: XOR it into the sign of both components
+#if defined(__CUDA_ARCH__)
+  a.x = __hiloint2double(__double2hiint(a.x) ^ (int)sign_bit, __double2loint(a.x));
+  a.y = __hiloint2double(__double2hiint(a.y) ^ (int)sign_bit, __double2loint(a.y));
+#else
+  if (sign_bit) { a.x = -a.x; a.y = -a.y; }
+#endif
+}
+
 // ---- phase: global -> shared ------------------------------------------------
-QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile,
-                         uint64_t base, uint32_t tid, uint32_t nthr_log2) {
-  const uint32_t T = P.T;
+// ghi[i] = qs_global_hi(P, i, ..) for i < 2^(T - nthr_log2)
+QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, uint64_t base, uint32_t tid,
+                         uint32_t nthr_log2, uint64_t glo, const uint64_t* ghi) {
   const uint32_t nthr = 1u << nthr_log2;
-  const uint32_t size = 1u << T;
-  const int lo_bits = (int)(T < nthr_log2 ? T : nthr_log2);
-  const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
+  const uint32_t size = 1u << P.T;
   const uint32_t slo = qs_swz(tid);
-  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) {
-    const uint64_t ghi = qs_scatter64(i, P.tile_bits + nthr_log2, (int)(T - lo_bits));
-    tile[slo ^ qs_swz(i << nthr_log2)] = state[base | glo | ghi];
-  }
+  const uint64_t b0 = base | glo;
+  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr)
+    tile[slo ^ qs_swz(i << nthr_log2)] = state[b0 | ghi[i]];
 }
 
 // ---- phase: shared -> global, with the pass's final sign block ---------------
-QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile,
-                          uint64_t base, uint32_t tid, uint32_t nthr_log2,
-                          uint32_t zmask, uint32_t gsign) {
+QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile, uint64_t base, uint32_t tid,
+                          uint32_t nthr_log2, uint64_t glo, const uint64_t* ghi, uint32_t zmask,
+                          uint32_t gsign) {
   const uint32_t T = P.T;
   const uint32_t nthr = 1u << nthr_log2;
   const uint32_t size = 1u << T;
   const QsStep& st = P.steps[P.nsteps - 1];
-  const bool has_sign = (st.n_oo | st.n_lo | st.n_ll) != 0;
-  const int lo_bits = (int)(T < nthr_log2 ? T : nthr_log2);
-  const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
   const uint32_t slo = qs_swz(tid);
+  const uint64_t b0 = base | glo;
+  if (!st.has_sign) {
+    for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr)
+      state[b0 | ghi[i]] = tile[slo ^ qs_swz(i << nthr_log2)];
+    return;
+  }
+  // j = tid | (i << nthr_log2): split the quadratic form accordingly
+  const int lo_bits = (int)(T < nthr_log2 ? T : nthr_log2);
+  uint32_t qlo = gsign ^ qs_par(tid & zmask);
+  for (int b = 0; b < lo_bits; ++b)
+    qlo ^= ((tid >> b) & 1u) & qs_par(tid & st.nsym[b] & ~((2u << b) - 1u));
   for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) {
-    const uint64_t ghi = qs_scatter64(i, P.tile_bits + nthr_log2, (int)(T - lo_bits));
-    qs_c128 v = tile[slo ^ qs_swz(i << nthr_log2)];
-    if (has_sign && qs_sign_of(P, st, j, zmask, gsign)) { v.x = -v.x; v.y = -v.y; }
-    state[base | glo | ghi] = v;
+    const uint32_t jhi = i << nthr_log2;
+    uint32_t q = qlo ^ qs_par(jhi & zmask);
+    uint32_t neigh = 0;
+    for (uint32_t p = nthr_log2; p < T; ++p) {
+      const uint32_t on = (jhi >> p) & 1u;
+      q ^= on & qs_par(jhi & st.nsym[p] & ~((2u << p) - 1u));
+      neigh ^= (0u - on) & st.nsym[p];
+    }
+    q ^= qs_par(tid & neigh);
+    qs_c128 v = tile[slo ^ qs_swz(jhi)];
+    qs_flip(v, q << 31);
+    state[b0 | ghi[i]] = v;
   }
 }
 
@@ -128,7 +183,15 @@ QS_HD void qs_mat2(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
 
 // ---- phase: one step ------------------------------------------------------------
 // R group bits; every work item is the 2^R amplitudes that differ only in them.
-template <int R>
+// Amplitude m of a work item has local index j0 ^ dep[m]; matrix factor f is bit
+// (R-1-f) of m and sits at local position gpos[f].
+//
+// Sign of amplitude m (plan.h):  g + z.(j0^dep) + Q(j0^dep)
+//   = [g + z.j0 + Q(j0)]  +  [z.dep + Q(dep)]  +  B(j0, dep)
+// The first bracket is one bit per work item (and splits again into a per-thread
+// and a per-iteration part), the second is a per-step table over m, and the
+// bilinear term is parity(m & W) with W_f = parity(j0 & nsym[gpos[f]]).
+template <int R, bool DENSE>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
                          uint32_t zmask, uint32_t gsign) {
   const QsStep& st = P.steps[s];
@@ -136,34 +199,71 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   const uint32_t nfree = T - R;
   const uint32_t nwork = 1u << nfree;
   const uint32_t nthr = 1u << nthr_log2;
-  const bool has_sign = (st.n_oo | st.n_lo | st.n_ll) != 0;
+  const bool has_sign = st.has_sign != 0;
   constexpr int NA = 1 << R;
 
-  // local-index offset of amplitude m of a work item (matrix factor f is the
-  // (R-1-f)-th bit of m and sits at local position gpos[f])
-  uint32_t dep[NA];
+  uint32_t sdep[NA];                       // swizzled slot offset of amplitude m
+  uint32_t ng[R];                          // neighbour mask of group bit f
+  uint32_t zg = 0;                         // z restricted to the group bits, in m-space
+  uint32_t qg = 0;                         // bit m: Q(dep[m]) (pairs inside the group)
+  {
+    uint32_t gp[R];
 #pragma unroll
-  for (int m = 0; m < NA; ++m) {
-    uint32_t d = 0;
+    for (int f = 0; f < R; ++f) {
+      gp[f] = st.gpos[f];
+      ng[f] = has_sign ? (uint32_t)st.nsym[gp[f]] : 0u;
+      zg |= ((zmask >> gp[f]) & 1u) << (R - 1 - f);
+    }
 #pragma unroll
-    for (int f = 0; f < R; ++f) d |= (uint32_t)((m >> (R - 1 - f)) & 1) << st.gpos[f];
-    dep[m] = d;
+    for (int m = 0; m < NA; ++m) {
+      uint32_t d = 0, q = 0;
+#pragma unroll
+      for (int f = 0; f < R; ++f) {
+        if ((m >> (R - 1 - f)) & 1) {
+          d |= 1u << gp[f];
+#pragma unroll
+          for (int f2 = f + 1; f2 < R; ++f2)
+            if ((m >> (R - 1 - f2)) & 1) q ^= (ng[f] >> gp[f2]) & 1u;
+        }
+      }
+      sdep[m] = qs_swz(d);
+      qg |= q << m;
+    }
   }
 
   const int lo_bits = (int)(nfree < nthr_log2 ? nfree : nthr_log2);
+  const int hi_bits = (int)(nfree - lo_bits);
   const uint32_t jlo = qs_scatter8(tid, st.fpos, lo_bits);
+  uint32_t alo = 0;
+  if (has_sign) alo = gsign ^ qs_par(jlo & zmask) ^ qs_quad_scattered(st, tid, st.fpos, lo_bits, jlo);
+
   for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthr) {
-    const uint32_t j0 = jlo | qs_scatter8(i, st.fpos + nthr_log2, (int)(nfree - lo_bits));
+    const uint32_t jhi = qs_scatter8(i, st.fpos + nthr_log2, hi_bits);
+    const uint32_t j0 = jlo | jhi;
     const uint32_t s0 = qs_swz(j0);
     qs_c128 a[NA];
 #pragma unroll
-    for (int m = 0; m < NA; ++m) a[m] = tile[s0 ^ qs_swz(dep[m])];
+    for (int m = 0; m < NA; ++m) a[m] = tile[s0 ^ sdep[m]];
     if (has_sign) {
+      const uint32_t ahi = qs_par(jhi & zmask) ^ qs_quad_scattered(st, i, st.fpos + nthr_log2, hi_bits, jhi);
+      const uint32_t cross = qs_par(jlo & qs_neigh_scattered(st, i, st.fpos + nthr_log2, hi_bits));
+      const uint32_t A = alo ^ ahi ^ cross;
+      uint32_t W = zg;
 #pragma unroll
-      for (int m = 0; m < NA; ++m)
-        if (qs_sign_of(P, st, j0 | dep[m], zmask, gsign)) { a[m].x = -a[m].x; a[m].y = -a[m].y; }
+      for (int f = 0; f < R; ++f) W ^= qs_par(j0 & ng[f]) << (R - 1 - f);
+      // signs of all 2^R amplitudes at once: bit m = A ^ qg_m ^ parity(m & W)
+      uint32_t sg = qg ^ (0u - A);
+#pragma unroll
+      for (int b = 0; b < R; ++b) {
+        uint32_t pat = 0;                  // bit m set iff bit b of m is set
+#pragma unroll
+        for (int m = 0; m < NA; ++m) pat |= (uint32_t)((m >> b) & 1) << m;
+        sg ^= (0u - ((W >> b) & 1u)) & pat;
+      }
+#pragma unroll
+      for (int m = 0; m < NA; ++m) qs_flip(a[m], (sg >> m) << 31);
     }
-    if (st.kind == QS_STEP_1Q) {
+    if (!DENSE || st.kind == QS_STEP_1Q) {
 #pragma unroll
       for (int f = 0; f < R; ++f) {
         const double* mat = P.coef + st.coef_off + 8 * f;
@@ -172,10 +272,13 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
         for (int m = 0; m < NA; ++m)
           if (!(m & bit)) qs_mat2(mat, a[m], a[m | bit]);
       }
-    } else {
-      const double* mat = P.coef + st.coef_off;
-      qs_c128 o[NA];
 #pragma unroll
+      for (int m = 0; m < NA; ++m) tile[s0 ^ sdep[m]] = a[m];
+    } else {
+      // dense 2^R x 2^R matrix: inputs are all in registers, so rows can be
+      // written back one at a time (rolled loop keeps the code small)
+      const double* mat = P.coef + st.coef_off;
+#pragma unroll 1
       for (int row = 0; row < NA; ++row) {
         double re = 0.0, im = 0.0;
 #pragma unroll
@@ -184,24 +287,24 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           re += mr * a[c].x - mi * a[c].y;
           im += mr * a[c].y + mi * a[c].x;
         }
-        o[row].x = re; o[row].y = im;
+        uint32_t d = 0;
+#pragma unroll
+        for (int f = 0; f < R; ++f) d |= (uint32_t)((row >> (R - 1 - f)) & 1) << st.gpos[f];
+        qs_c128 o; o.x = re; o.y = im;
+        tile[s0 ^ qs_swz(d)] = o;
       }
-#pragma unroll
-      for (int m = 0; m < NA; ++m) a[m] = o[m];
     }
-#pragma unroll
-    for (int m = 0; m < NA; ++m) tile[s0 ^ qs_swz(dep[m])] = a[m];
   }
 }
 
 // MAXR bounds the instantiated group sizes (and with them the register budget
-// of the calling kernel).
-template <int MAXR>
+// of the calling kernel); DENSE says whether dense (k >= 2) steps may occur.
+template <int MAXR, bool DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
                              uint32_t zmask, uint32_t gsign) {
   const int r = P.steps[s].r;
-  if (r == 1) qs_phase_step<1>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (r == 2) qs_phase_step<2>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (r == 3) qs_phase_step<3>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (MAXR >= 4 && r == 4) qs_phase_step<(MAXR >= 4 ? 4 : 1)>(P, s, tile, tid, nthr_log2, zmask, gsign);
+  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, gsign);
+  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
+  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
+  else if (MAXR >= 4 && r == 4) qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
 }
