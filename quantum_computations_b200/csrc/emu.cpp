@@ -20,27 +20,41 @@ int64_t g_launches = 0;
 
 void emu_pass(const QsPass& P, qs_c128* state, int n) {
   const uint64_t ntiles = 1ull << (n - (int)P.T);
-  std::vector<qs_c128> tile((size_t)1 << P.T);
-  std::vector<uint32_t> zmask(P.nsteps), gsign(P.nsteps);
   const int nsteps = (int)P.nsteps;
+  std::vector<qs_c128> tile((size_t)1 << P.T);
+  std::vector<uint32_t> zmask(nsteps + 2, 0);
+  std::vector<QsStepTab> tab(nsteps ? nsteps : 1);
+  QsIoTab io;
   bool dense = false;
-  for (int s = 0; s < nsteps; ++s) dense |= P.steps[s].kind == QS_STEP_DENSE;
-  uint64_t ghi[1 << (QS_MAX_T - QS_THREADS_LOG2)];
-  for (uint32_t i = 0; i < (1u << (QS_MAX_T - QS_THREADS_LOG2)); ++i) ghi[i] = qs_global_hi(P, i, QS_THREADS_LOG2);
+  for (int s = 0; s < nsteps; ++s) {
+    dense |= P.steps[s].kind == QS_STEP_DENSE;
+    for (int e = 0; e < 48; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
+  }
+  for (uint32_t i = 0; i < QS_MAX_ITER; ++i) qs_build_io_tab(P, i, &io, QS_THREADS_LOG2);
+  io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
+  std::vector<uint64_t> glo(QS_THREADS);
+  std::vector<uint32_t> fin_qlo(QS_THREADS);
+  for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
+    glo[tid] = qs_scatter64(tid, P.tile_bits, lo_bits);
+    fin_qlo[tid] = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
+  }
   for (uint64_t t = 0; t < ntiles; ++t) {
     const uint64_t base = qs_tile_base(P, t);
-    for (int s = 0; s < nsteps; ++s) qs_sign_prepare(P, s, base, &zmask[s], &gsign[s]);
+    for (int s = 0; s < nsteps; ++s)
+      if (P.steps[s].has_sign) zmask[s] = qs_step_zmask(P, s, base);
+    if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, qs_global_lo(P, tid, QS_THREADS_LOG2), ghi);
-    for (int s = 0; s + 1 < nsteps; ++s)
+      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io);
+    for (int s = 0; s < nsteps; ++s)
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
         // same variant selection as launch_pass() in kernels.cu
-        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
-        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], gsign[s]);
+        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
+        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
       }
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, qs_global_lo(P, tid, QS_THREADS_LOG2), ghi,
-                     zmask[nsteps - 1], gsign[nsteps - 1]);
+      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io, fin_qlo[tid],
+                     zmask[nsteps], zmask[nsteps + 1]);
   }
   ++g_launches;
 }

@@ -75,28 +75,37 @@ __global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* tile = reinterpret_cast<qs_c128*>(qs_smem);
-  __shared__ uint32_t s_zmask[QS_MAX_STEPS];
-  __shared__ uint32_t s_gsign[QS_MAX_STEPS];
-  __shared__ uint64_t s_ghi[1 << (QS_MAX_T - QS_THREADS_LOG2)];
+  __shared__ QsStepTab s_tab[QS_MAX_STEPS];
+  __shared__ QsIoTab s_io;
+  __shared__ uint32_t s_zmask[QS_MAX_STEPS + 2];   // [nsteps], then final z, final g
   const uint32_t tid = threadIdx.x;
   const int nsteps = (int)P.nsteps;
 
-  // tile-independent pieces of the global addresses
-  const uint64_t glo = qs_global_lo(P, tid, QS_THREADS_LOG2);
-  if (tid < (1u << (QS_MAX_T - QS_THREADS_LOG2))) s_ghi[tid] = qs_global_hi(P, tid, QS_THREADS_LOG2);
+  // tile-independent tables, once per launch (the grid is persistent)
+  for (int e = (int)tid; e < nsteps * 48; e += QS_THREADS)
+    qs_build_step_tab(P, e / 48, e % 48, &s_tab[e / 48], QS_THREADS_LOG2);
+  if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
+  if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
+  const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
+  const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   __syncthreads();
 
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t base = qs_tile_base(P, t);
-    if ((int)tid < nsteps) qs_sign_prepare(P, (int)tid, base, &s_zmask[tid], &s_gsign[tid]);
-    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_ghi);
+    if ((int)tid < nsteps) {
+      if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zmask(P, (int)tid, base);
+    } else if ((int)tid == nsteps && P.fin_has_sign) {
+      qs_fin_prepare(P, base, &s_zmask[nsteps], &s_zmask[nsteps + 1]);
+    }
+    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_io);
     __syncthreads();
-    for (int s = 0; s + 1 < nsteps; ++s) {
-      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_gsign[s]);
+    for (int s = 0; s < nsteps; ++s) {
+      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s]);
       __syncthreads();
     }
-    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_ghi, s_zmask[nsteps - 1],
-                   s_gsign[nsteps - 1]);
+    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
+                   s_zmask[nsteps + 1]);
     __syncthreads();
   }
 }

@@ -9,18 +9,24 @@
 // global access touches runs of 2^L consecutive complex128 amplitudes.
 //
 // A *step* is one shared-memory round trip: every thread pulls 2^r amplitudes
-// (spanning r "group" bits of the tile) into registers, optionally flips signs
-// (a block of CZ/Z gates, which may involve ANY index bit), applies either r
-// independent 2x2 matrices or one dense 2^r x 2^r matrix, and stores back.
+// (spanning r "group" bits of the tile) into registers, optionally flips signs,
+// applies either r independent 2x2 matrices or one dense 2^r x 2^r matrix, and
+// stores back.
 //
-// Sign blocks.  A block of CZ/Z gates multiplies amplitude i by (-1)^q(i) with q
-// a quadratic form over GF(2) in the index bits.  Relative to a tile it splits
-//   q = g  +  z . j  +  Q(j)           (j = local index inside the tile)
-// into a tile-uniform bit g (pairs of outer bits), a linear part z (local Z
-// gates: `zconst`; CZ between a local and an outer bit: the `lo` pairs, resolved
-// per tile) and a quadratic part Q over local bits only, stored as symmetric
-// neighbour masks `nsym`.  The kernels evaluate it with a handful of popcounts
-// per work item instead of a loop over pairs per amplitude (tile_exec.h).
+// Sign blocks.  CZ and Z gates multiply amplitude i by (-1)^q(i), q a quadratic
+// form over GF(2) in the index bits -- no memory traffic, any qubits.  They
+// commute with every matrix that does not touch their bits, so the planner
+// DEFERS each pending pair to the first later step whose group contains one of
+// its bits (or to the pass's final block, applied on the way back to HBM).  A
+// step's block therefore only holds pairs that touch its group bits, and its sign
+// for amplitude m of a work item at local index j0 is
+//     parity(m & W(j0)) + qg(m),
+//     W_f = z_f + parity(j0 & ng[f])        (f = group factor)
+// with ng[f] the in-tile partners of group bit f, z_f a Z on it (a local Z, or a
+// CZ with an outer bit that is 1 for this tile), and qg the pairs inside the
+// group: a few popcounts per work item.  Only the final block evaluates a full
+// quadratic form  g + z.j + Q(j)  (tile-uniform bit g from pairs of outer bits,
+// linear mask z, symmetric neighbour masks nsym).
 //
 // Index-bit convention inside the library: bit b of the linear index.  The
 // reference numbers qubits from the most significant end, so reference qubit q
@@ -30,39 +36,46 @@
 
 #define QS_MAX_T        13     // largest tile: 2^13 amplitudes = 128 KiB
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
-#define QS_MAX_STEPS    56
+#define QS_MAX_STEPS    48
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #define QS_THREADS_LOG2 8
 #define QS_THREADS      (1 << QS_THREADS_LOG2)
+#define QS_MAX_ITER     (1 << (QS_MAX_T - QS_THREADS_LOG2))   // amplitudes per thread in load/store
 
 enum QsStepKind : uint8_t {
   QS_STEP_1Q    = 0,   // r independent 2x2 matrices, one per group bit
-  QS_STEP_DENSE = 1,   // one 2^r x 2^r matrix on the r group bits
-  QS_STEP_SIGN  = 2    // sign block only (fused into the final store)
+  QS_STEP_DENSE = 1    // one 2^r x 2^r matrix on the r group bits
 };
 
 struct QsStep {
   uint8_t  kind;
-  uint8_t  r;                    // number of group bits (0 for QS_STEP_SIGN)
+  uint8_t  r;                    // number of group bits
   uint8_t  gpos[QS_MAX_R];       // local position of matrix factor f (f=0: most significant)
   uint8_t  fpos[QS_MAX_T];       // the T-r free local positions, in thread-scatter order
   uint8_t  has_sign;             // 1 if the step's sign block is not empty
   uint16_t coef_off;             // first coefficient (in doubles) in QsPass::coef
-  // sign block applied to the amplitudes as they are loaded for this step
-  uint16_t pair_off;             // first pair (index into QsPass::pairs, 2 bytes each)
-  uint8_t  n_oo;                 // pairs with both bits outside the tile (global bit numbers)
-  uint8_t  n_lo;                 // pairs (local position, outer global bit)
-  uint16_t zconst;               // local positions carrying a Z
-  uint16_t nsym[QS_MAX_T];       // nsym[p]: local positions CZ-coupled to local position p
+  // sign block (only pairs touching a group bit)
+  uint16_t pair_off;             // first (local position, outer global bit) pair in QsPass::pairs
+  uint16_t n_lo;
+  uint16_t zconst;               // local positions (group bits) carrying a Z
+  uint16_t ng[QS_MAX_R];         // in-tile CZ partners (local positions) of group factor f
 };
 
 struct QsPass {
   uint32_t T;                    // tile bits
-  uint32_t nsteps;               // steps[nsteps-1] is always a QS_STEP_SIGN (maybe empty)
+  uint32_t nsteps;
   uint32_t ncoef;
   uint32_t npairs;
   uint8_t  tile_bits[16];        // ascending global bit numbers of the local positions
+  // final sign block, applied while storing back to global memory
+  uint8_t  fin_has_sign;
+  uint8_t  pad0;
+  uint16_t fin_pair_off;         // first pair: n_oo (outer, outer) then n_lo (local, outer)
+  uint16_t fin_n_oo;
+  uint16_t fin_n_lo;
+  uint16_t fin_zconst;
+  uint16_t fin_nsym[QS_MAX_T];   // fin_nsym[p]: local positions CZ-coupled to local position p
   QsStep   steps[QS_MAX_STEPS];
   uint8_t  pairs[QS_MAX_PAIRS * 2];
   double   coef[QS_MAX_COEF];
@@ -70,3 +83,20 @@ struct QsPass {
 
 // CUDA kernel parameters are limited to 32764 bytes (CUDA >= 12.1, sm_70+).
 static_assert(sizeof(QsPass) <= 32000, "QsPass must fit in the kernel parameter space");
+
+// Per-step lookup tables, built once per kernel launch in shared memory (they do
+// not depend on the tile): where the thread id and the per-thread iteration
+// counter land inside the tile.
+struct QsStepTab {
+  uint16_t jA[16];               // local-index bits of thread-id nibble 0
+  uint16_t jB[16];               // local-index bits of thread-id nibble 1
+  uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
+};
+
+// Tables for the load/store phases and the final sign block.
+struct QsIoTab {
+  uint64_t ghi[QS_MAX_ITER];     // global-index bits of iteration i
+  uint16_t shi[QS_MAX_ITER];     // swz(i << QS_THREADS_LOG2)
+  uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
+  uint32_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
+};

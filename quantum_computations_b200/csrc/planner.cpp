@@ -237,50 +237,54 @@ struct Walker {
     int step_r[QS_MAX_STEPS];                // members of a 1Q step; -1 = dense step (closed)
     int last_dense[64], last_sign[64];
     for (int b = 0; b < 64; ++b) { last_dense[b] = -1; last_sign[b] = 0; }
-    uint64_t pend_mask = 0;                  // bits touched by the pending sign pairs
-    uint8_t pend[256][2];                    // sign pairs waiting for the next step
+    // Sign pairs taken but not yet attached: each waits for the first later step
+    // whose group contains one of its bits, else for the pass's final block.
+    uint64_t pend_mask = 0;
+    uint8_t pend[256][2];
     int npend = 0;
 
-    auto flush_pairs_into = [&](QsStep* st) {
-      if (st) {
-        uint8_t* dst = pass->pairs + 2 * npairs;
-        int w = 0, n_oo = 0, n_lo = 0, n_ll = 0;
-        for (int p = 0; p < npend; ++p) {        // both bits outside the tile
-          const int a = pend[p][0], b = pend[p][1];
-          if (lpos[a] < 0 && lpos[b] < 0) { dst[w++] = (uint8_t)a; dst[w++] = (uint8_t)b; ++n_oo; }
+    // attach to the step being created (group = op bits) every pending pair that
+    // touches a group bit
+    auto attach_pairs = [&](QsStep* st, const Op& op, uint64_t gmask) {
+      int kept = 0, n_lo = 0;
+      uint64_t new_mask = 0;
+      uint8_t* dst = pass ? pass->pairs + 2 * npairs : nullptr;
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        const bool ga = (gmask >> a) & 1, gb = (gmask >> b) & 1;
+        if (!ga && !gb) {
+          pend[kept][0] = (uint8_t)a; pend[kept][1] = (uint8_t)b; ++kept;
+          new_mask |= (1ull << a) | (1ull << b);
+          continue;
         }
-        for (int p = 0; p < npend; ++p) {        // one inside: (local position, outer bit)
-          const int a = pend[p][0], b = pend[p][1];
-          if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
-            const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
-            dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
-          }
+        last_sign[a] = nsteps; last_sign[b] = nsteps;
+        const bool mixed = (lpos[a] < 0) != (lpos[b] < 0);
+        if (!st) {
+          if (mixed) ++n_lo;
+          continue;
         }
-        for (int p = 0; p < npend; ++p) {        // both inside: neighbour masks / local Z
-          const int a = pend[p][0], b = pend[p][1];
-          if (lpos[a] >= 0 && lpos[b] >= 0) {
-            if (a == b) {
-              st->zconst ^= (uint16_t)(1u << lpos[a]);
-            } else {
-              st->nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
-              st->nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
-            }
-            ++n_ll;
-          }
+        st->has_sign = 1;
+        auto factor_of = [&](int bit) {
+          for (int f = 0; f < op.k; ++f)
+            if (op.bits[f] == bit) return f;
+          return 0;
+        };
+        if (a == b) {
+          st->zconst ^= (uint16_t)(1u << lpos[a]);
+        } else if (!mixed) {
+          if (ga) st->ng[factor_of(a)] ^= (uint16_t)(1u << lpos[b]);
+          if (gb) st->ng[factor_of(b)] ^= (uint16_t)(1u << lpos[a]);
+        } else {
+          const int in = ga ? a : b, outb = ga ? b : a;     // the group bit is inside the tile
+          dst[2 * n_lo] = (uint8_t)lpos[in]; dst[2 * n_lo + 1] = (uint8_t)outb; ++n_lo;
         }
-        st->pair_off = (uint16_t)npairs;
-        st->n_oo = (uint8_t)n_oo; st->n_lo = (uint8_t)n_lo;
-        st->has_sign = (n_oo + n_lo + n_ll) > 0 ? 1 : 0;
-        (void)w;
       }
-      npairs += npend;
-      npend = 0;
-      for (int b = 0; b < n; ++b)
-        if (pend_mask >> b & 1) last_sign[b] = nsteps;    // nsteps = index of the receiving step
-      pend_mask = 0;
+      if (st) { st->pair_off = (uint16_t)npairs; st->n_lo = (uint16_t)n_lo; }
+      npairs += n_lo;
+      npend = kept;
+      pend_mask = new_mask;
     };
 
-    const int max_steps = QS_MAX_STEPS - 1;   // the last slot is the final sign step
     for (size_t i = first; i < ops.size(); ++i) {
       if (done[i]) continue;
       if (!pass && ++visited > opt.lookahead) break;
@@ -289,7 +293,7 @@ struct Walker {
       if (op.kind == OP_SIGN) {
         const bool room = npairs + npend + 1 <= QS_MAX_PAIRS && npend < 250;
         if ((m & blocked_full) == 0 && room) {
-          // CZ is an involution: a repeated pair cancels
+          // CZ is an involution: a repeated pending pair cancels
           const int a = std::min(op.bits[0], op.bits[1]), b = std::max(op.bits[0], op.bits[1]);
           int hit = -1;
           for (int p = 0; p < npend; ++p)
@@ -301,7 +305,7 @@ struct Walker {
             pend[npend][0] = (uint8_t)a; pend[npend][1] = (uint8_t)b;
             ++npend;
           }
-          pend_mask |= m;
+          pend_mask |= m;      // conservative after a cancellation
           ++sign_taken;
           if (taken_idx) taken_idx->push_back(i);
         } else {
@@ -321,7 +325,7 @@ struct Walker {
           }
           if (join < 0) {
             const int need = (op.k == 1) ? 8 * opt.max_group : 2 * (1 << op.k) * (1 << op.k);
-            if (nsteps >= max_steps || ncoef + need > QS_MAX_COEF) take = false;
+            if (nsteps >= QS_MAX_STEPS || ncoef + need > QS_MAX_COEF) take = false;
           }
         }
         if (take && join >= 0) {
@@ -337,7 +341,7 @@ struct Walker {
         } else if (take) {
           QsStep* st = pass ? &pass->steps[nsteps] : nullptr;
           if (st) *st = QsStep{};
-          flush_pairs_into(st);
+          attach_pairs(st, op, m);
           const int dim = 1 << op.k;
           if (st) {
             st->coef_off = (uint16_t)ncoef;
@@ -370,11 +374,36 @@ struct Walker {
     }
 
     if (pass) {
-      QsStep& fin = pass->steps[nsteps];
-      fin = QsStep{};
-      fin.kind = QS_STEP_SIGN;
-      flush_pairs_into(&fin);
-      ++nsteps;
+      // whatever is still pending goes into the final block
+      uint8_t* dst = pass->pairs + 2 * npairs;
+      int w = 0, n_oo = 0, n_lo = 0;
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if (lpos[a] < 0 && lpos[b] < 0) { dst[w++] = (uint8_t)a; dst[w++] = (uint8_t)b; ++n_oo; }
+      }
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
+          const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
+          dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
+        }
+      }
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if (lpos[a] >= 0 && lpos[b] >= 0) {
+          if (a == b) {
+            pass->fin_zconst ^= (uint16_t)(1u << lpos[a]);
+          } else {
+            pass->fin_nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
+            pass->fin_nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
+          }
+        }
+      }
+      pass->fin_has_sign = npend > 0 ? 1 : 0;
+      pass->fin_pair_off = (uint16_t)npairs;
+      pass->fin_n_oo = (uint16_t)n_oo;
+      pass->fin_n_lo = (uint16_t)n_lo;
+      npairs += n_oo + n_lo;
       pass->nsteps = (uint32_t)nsteps;
       pass->ncoef = (uint32_t)ncoef;
       pass->npairs = (uint32_t)npairs;
@@ -491,16 +520,10 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
     for (uint32_t s = 0; s < P.nsteps; ++s) {
       QsStep& st = P.steps[s];
       order_free_positions(st, (int)P.T);
-      if (st.kind != QS_STEP_SIGN) {
-        stats.n_steps++;
-        stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
-      }
-      {
-        int ll = __builtin_popcount(st.zconst);
-        for (uint32_t p2 = 0; p2 < P.T; ++p2) ll += __builtin_popcount((uint32_t)st.nsym[p2] & ~((2u << p2) - 1u) & 0xffffu);
-        stats.n_sign += st.n_oo + st.n_lo + ll;
-      }
+      stats.n_steps++;
+      stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
     }
+    for (size_t idx : taken) stats.n_sign += ops[idx].kind == OP_SIGN ? 1 : 0;
     stats.n_passes++;
     out->items.push_back(std::move(it));
   }

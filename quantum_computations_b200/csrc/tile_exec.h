@@ -58,58 +58,72 @@ QS_HD uint64_t qs_tile_base(const QsPass& P, uint64_t tile) {
   return base;
 }
 
-// Global-index contribution of the thread id (local bits 0..nthr_log2-1) and of
-// the per-thread iteration counter i (the remaining local bits).  Both are the
-// same for every tile of a pass, so the kernel computes them once.
-QS_HD uint64_t qs_global_lo(const QsPass& P, uint32_t tid, uint32_t nthr_log2) {
-  const int lo_bits = (int)(P.T < nthr_log2 ? P.T : nthr_log2);
-  return qs_scatter64(tid, P.tile_bits, lo_bits);
-}
-QS_HD uint64_t qs_global_hi(const QsPass& P, uint32_t i, uint32_t nthr_log2) {
-  if (P.T <= nthr_log2) return 0;
-  return qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2));
-}
-
-// ---- sign blocks ------------------------------------------------------------------------
-// Per tile and per step: the tile-uniform bit g and the linear mask z (plan.h).
-QS_HD void qs_sign_prepare(const QsPass& P, int s, uint64_t base, uint32_t* zmask, uint32_t* gsign) {
-  const QsStep& st = P.steps[s];
-  const uint8_t* pr = P.pairs + 2 * (uint32_t)st.pair_off;
-  uint32_t g = 0, z = st.zconst;
-  for (int i = 0; i < st.n_oo; ++i, pr += 2)
-    g ^= (uint32_t)((base >> pr[0]) & (base >> pr[1]) & 1ull);
-  for (int i = 0; i < st.n_lo; ++i, pr += 2)
-    z ^= (uint32_t)((base >> pr[1]) & 1ull) << pr[0];
-  *zmask = z;
-  *gsign = g;
-}
-
-// Q(x) for x = the scatter of the low `count` bits of v over pos[]: every coupled
-// pair inside x counted once (the partner with the higher position).
-QS_HD uint32_t qs_quad_scattered(const QsStep& st, uint32_t v, const uint8_t* pos, int count, uint32_t x) {
+// Q(x) of the final block: every coupled pair inside x counted once.
+QS_HD uint32_t qs_fin_quad(const QsPass& P, uint32_t x) {
   uint32_t q = 0;
-  for (int b = 0; b < count; ++b) {
-    const uint32_t p = pos[b];
-    const uint32_t up = ~((2u << p) - 1u);
-    q ^= ((v >> b) & 1u) & qs_par(x & st.nsym[p] & up);
+  for (uint32_t p = 0; p < P.T; ++p)
+    q ^= ((x >> p) & 1u) & qs_par(x & P.fin_nsym[p] & ~((2u << p) - 1u));
+  return q;
+}
+QS_HD uint32_t qs_fin_neigh(const QsPass& P, uint32_t x) {
+  uint32_t m = 0;
+  for (uint32_t p = 0; p < P.T; ++p) m ^= (0u - ((x >> p) & 1u)) & P.fin_nsym[p];
+  return m;
+}
+
+// ---- per-launch tables (tile independent) -----------------------------------------------
+// Entry e (0..47) of a step's table: 0..15 -> jA, 16..31 -> jB, 32..47 -> hi.
+QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint32_t nthr_log2) {
+  const QsStep& st = P.steps[s];
+  const int nfree = (int)P.T - st.r;
+  const int lo_bits = nfree < (int)nthr_log2 ? nfree : (int)nthr_log2;
+  if (e < 16) {
+    const int c = lo_bits < 4 ? lo_bits : 4;
+    tab->jA[e] = (uint16_t)qs_scatter8((uint32_t)e, st.fpos, c);
+  } else if (e < 32) {
+    const int c = lo_bits - 4 < 0 ? 0 : (lo_bits - 4 > 4 ? 4 : lo_bits - 4);
+    tab->jB[e - 16] = (uint16_t)qs_scatter8((uint32_t)(e - 16), st.fpos + 4, c);
+  } else {
+    const uint32_t jhi = qs_scatter8((uint32_t)(e - 32), st.fpos + nthr_log2, nfree - lo_bits);
+    tab->hi[e - 32] = jhi | (qs_swz(jhi) << 16);
+  }
+}
+
+QS_HD void qs_build_io_tab(const QsPass& P, uint32_t i, QsIoTab* io, uint32_t nthr_log2) {
+  const uint32_t jhi = i << nthr_log2;
+  io->ghi[i] = (P.T <= nthr_log2) ? 0ull : qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2));
+  io->shi[i] = (uint16_t)qs_swz(jhi & ((1u << P.T) - 1u));
+  io->fin_neigh[i] = 0;
+  if (P.fin_has_sign && jhi < (1u << P.T)) io->fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
+}
+// fin_q is a bit mask over i; build it with one thread (or sequentially on the host)
+QS_HD uint32_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
+  uint32_t q = 0;
+  if (!P.fin_has_sign) return 0;
+  for (uint32_t i = 0; i < QS_MAX_ITER; ++i) {
+    const uint32_t jhi = i << nthr_log2;
+    if (jhi < (1u << P.T)) q |= qs_fin_quad(P, jhi) << i;
   }
   return q;
 }
 
-// XOR of the neighbour masks of the set bits of the scattered value.
-QS_HD uint32_t qs_neigh_scattered(const QsStep& st, uint32_t v, const uint8_t* pos, int count) {
-  uint32_t m = 0;
-  for (int b = 0; b < count; ++b) m ^= (0u - ((v >> b) & 1u)) & st.nsym[pos[b]];
-  return m;
+// ---- per-tile sign data ---------------------------------------------------------------------
+// Step s: linear mask z over local positions (only the group bits matter).
+QS_HD uint32_t qs_step_zmask(const QsPass& P, int s, uint64_t base) {
+  const QsStep& st = P.steps[s];
+  const uint8_t* pr = P.pairs + 2 * (uint32_t)st.pair_off;
+  uint32_t z = st.zconst;
+  for (int i = 0; i < st.n_lo; ++i, pr += 2) z ^= (uint32_t)((base >> pr[1]) & 1ull) << pr[0];
+  return z;
 }
-
-// Reference implementation of the whole sign (used by the host emulator's
-// self-check and by nothing on the hot path): g + z.j + Q(j).
-QS_HD uint32_t qs_sign_slow(const QsStep& st, uint32_t T, uint32_t j, uint32_t zmask, uint32_t gsign) {
-  uint32_t sg = gsign ^ qs_par(j & zmask);
-  for (uint32_t p = 0; p < T; ++p)
-    if ((j >> p) & 1u) sg ^= qs_par(j & st.nsym[p] & ~((2u << p) - 1u));
-  return sg;
+// Final block: tile-uniform bit g and linear mask z.
+QS_HD void qs_fin_prepare(const QsPass& P, uint64_t base, uint32_t* zmask, uint32_t* gsign) {
+  const uint8_t* pr = P.pairs + 2 * (uint32_t)P.fin_pair_off;
+  uint32_t g = 0, z = P.fin_zconst;
+  for (int i = 0; i < P.fin_n_oo; ++i, pr += 2) g ^= (uint32_t)((base >> pr[0]) & (base >> pr[1]) & 1ull);
+  for (int i = 0; i < P.fin_n_lo; ++i, pr += 2) z ^= (uint32_t)((base >> pr[1]) & 1ull) << pr[0];
+  *zmask = z;
+  *gsign = g;
 }
 
 QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
@@ -123,50 +137,36 @@ QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
 }
 
 // ---- phase: global -> shared ------------------------------------------------
-// ghi[i] = qs_global_hi(P, i, ..) for i < 2^(T - nthr_log2)
 QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, uint64_t base, uint32_t tid,
-                         uint32_t nthr_log2, uint64_t glo, const uint64_t* ghi) {
+                         uint32_t nthr_log2, uint64_t glo, const QsIoTab& io) {
   const uint32_t nthr = 1u << nthr_log2;
   const uint32_t size = 1u << P.T;
   const uint32_t slo = qs_swz(tid);
   const uint64_t b0 = base | glo;
-  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr)
-    tile[slo ^ qs_swz(i << nthr_log2)] = state[b0 | ghi[i]];
+  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) tile[slo ^ io.shi[i]] = state[b0 | io.ghi[i]];
 }
 
 // ---- phase: shared -> global, with the pass's final sign block ---------------
+// fin_qlo = Q(tid) of the final block (tile independent, computed once per launch).
 QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile, uint64_t base, uint32_t tid,
-                          uint32_t nthr_log2, uint64_t glo, const uint64_t* ghi, uint32_t zmask,
-                          uint32_t gsign) {
-  const uint32_t T = P.T;
+                          uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, uint32_t fin_qlo,
+                          uint32_t zmask, uint32_t gsign) {
   const uint32_t nthr = 1u << nthr_log2;
-  const uint32_t size = 1u << T;
-  const QsStep& st = P.steps[P.nsteps - 1];
+  const uint32_t size = 1u << P.T;
   const uint32_t slo = qs_swz(tid);
   const uint64_t b0 = base | glo;
-  if (!st.has_sign) {
-    for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr)
-      state[b0 | ghi[i]] = tile[slo ^ qs_swz(i << nthr_log2)];
+  if (!P.fin_has_sign) {
+    for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) state[b0 | io.ghi[i]] = tile[slo ^ io.shi[i]];
     return;
   }
-  // j = tid | (i << nthr_log2): split the quadratic form accordingly
-  const int lo_bits = (int)(T < nthr_log2 ? T : nthr_log2);
-  uint32_t qlo = gsign ^ qs_par(tid & zmask);
-  for (int b = 0; b < lo_bits; ++b)
-    qlo ^= ((tid >> b) & 1u) & qs_par(tid & st.nsym[b] & ~((2u << b) - 1u));
+  // j = tid | (i << nthr_log2):  g + z.j + Q(tid) + Q(jhi) + B(tid, jhi)
+  const uint32_t qlo = gsign ^ fin_qlo ^ qs_par(tid & zmask);
+  const uint32_t zhi = zmask >> nthr_log2;
   for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) {
-    const uint32_t jhi = i << nthr_log2;
-    uint32_t q = qlo ^ qs_par(jhi & zmask);
-    uint32_t neigh = 0;
-    for (uint32_t p = nthr_log2; p < T; ++p) {
-      const uint32_t on = (jhi >> p) & 1u;
-      q ^= on & qs_par(jhi & st.nsym[p] & ~((2u << p) - 1u));
-      neigh ^= (0u - on) & st.nsym[p];
-    }
-    q ^= qs_par(tid & neigh);
-    qs_c128 v = tile[slo ^ qs_swz(jhi)];
+    const uint32_t q = qlo ^ qs_par(i & zhi) ^ ((io.fin_q >> i) & 1u) ^ qs_par(tid & io.fin_neigh[i]);
+    qs_c128 v = tile[slo ^ io.shi[i]];
     qs_flip(v, q << 31);
-    state[b0 | ghi[i]] = v;
+    state[b0 | io.ghi[i]] = v;
   }
 }
 
@@ -184,34 +184,27 @@ QS_HD void qs_mat2(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
 // ---- phase: one step ------------------------------------------------------------
 // R group bits; every work item is the 2^R amplitudes that differ only in them.
 // Amplitude m of a work item has local index j0 ^ dep[m]; matrix factor f is bit
-// (R-1-f) of m and sits at local position gpos[f].
-//
-// Sign of amplitude m (plan.h):  g + z.(j0^dep) + Q(j0^dep)
-//   = [g + z.j0 + Q(j0)]  +  [z.dep + Q(dep)]  +  B(j0, dep)
-// The first bracket is one bit per work item (and splits again into a per-thread
-// and a per-iteration part), the second is a per-step table over m, and the
-// bilinear term is parity(m & W) with W_f = parity(j0 & nsym[gpos[f]]).
+// (R-1-f) of m and sits at local position gpos[f].  Sign of amplitude m:
+// parity(m & W) + qg(m) with W_f = z_f + parity(j0 & ng[f])   (plan.h).
 template <int R, bool DENSE>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                         uint32_t zmask, uint32_t gsign) {
+                         uint32_t zmask, const QsStepTab& tab) {
   const QsStep& st = P.steps[s];
-  const uint32_t T = P.T;
-  const uint32_t nfree = T - R;
-  const uint32_t nwork = 1u << nfree;
+  const uint32_t nwork = 1u << (P.T - R);
   const uint32_t nthr = 1u << nthr_log2;
   const bool has_sign = st.has_sign != 0;
   constexpr int NA = 1 << R;
 
   uint32_t sdep[NA];                       // swizzled slot offset of amplitude m
-  uint32_t ng[R];                          // neighbour mask of group bit f
-  uint32_t zg = 0;                         // z restricted to the group bits, in m-space
-  uint32_t qg = 0;                         // bit m: Q(dep[m]) (pairs inside the group)
+  uint32_t ng[R];                          // in-tile partners of group factor f
+  uint32_t zg = 0;                         // Z on the group bits, in m-space
+  uint32_t qg = 0;                         // bit m: pairs inside the group
   {
     uint32_t gp[R];
 #pragma unroll
     for (int f = 0; f < R; ++f) {
       gp[f] = st.gpos[f];
-      ng[f] = has_sign ? (uint32_t)st.nsym[gp[f]] : 0u;
+      ng[f] = has_sign ? (uint32_t)st.ng[f] : 0u;
       zg |= ((zmask >> gp[f]) & 1u) << (R - 1 - f);
     }
 #pragma unroll
@@ -231,28 +224,22 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
     }
   }
 
-  const int lo_bits = (int)(nfree < nthr_log2 ? nfree : nthr_log2);
-  const int hi_bits = (int)(nfree - lo_bits);
-  const uint32_t jlo = qs_scatter8(tid, st.fpos, lo_bits);
-  uint32_t alo = 0;
-  if (has_sign) alo = gsign ^ qs_par(jlo & zmask) ^ qs_quad_scattered(st, tid, st.fpos, lo_bits, jlo);
+  const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 15u];
+  const uint32_t slo = qs_swz(jlo);
 
   for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthr) {
-    const uint32_t jhi = qs_scatter8(i, st.fpos + nthr_log2, hi_bits);
-    const uint32_t j0 = jlo | jhi;
-    const uint32_t s0 = qs_swz(j0);
+    const uint32_t hi = tab.hi[i];
+    const uint32_t j0 = jlo | (hi & 0xffffu);
+    const uint32_t s0 = slo ^ (hi >> 16);
     qs_c128 a[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) a[m] = tile[s0 ^ sdep[m]];
     if (has_sign) {
-      const uint32_t ahi = qs_par(jhi & zmask) ^ qs_quad_scattered(st, i, st.fpos + nthr_log2, hi_bits, jhi);
-      const uint32_t cross = qs_par(jlo & qs_neigh_scattered(st, i, st.fpos + nthr_log2, hi_bits));
-      const uint32_t A = alo ^ ahi ^ cross;
       uint32_t W = zg;
 #pragma unroll
       for (int f = 0; f < R; ++f) W ^= qs_par(j0 & ng[f]) << (R - 1 - f);
-      // signs of all 2^R amplitudes at once: bit m = A ^ qg_m ^ parity(m & W)
-      uint32_t sg = qg ^ (0u - A);
+      // signs of all 2^R amplitudes at once: bit m = qg_m ^ parity(m & W)
+      uint32_t sg = qg;
 #pragma unroll
       for (int b = 0; b < R; ++b) {
         uint32_t pat = 0;                  // bit m set iff bit b of m is set
@@ -301,10 +288,10 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 // of the calling kernel); DENSE says whether dense (k >= 2) steps may occur.
 template <int MAXR, bool DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                             uint32_t zmask, uint32_t gsign) {
+                             uint32_t zmask, const QsStepTab& tab) {
   const int r = P.steps[s].r;
-  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
-  else if (MAXR >= 4 && r == 4) qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zmask, gsign);
+  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, tab);
+  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
+  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
+  else if (MAXR >= 4 && r == 4) qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
 }
