@@ -28,7 +28,7 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   bool dense = false;
   for (int s = 0; s < nsteps; ++s) {
     dense |= P.steps[s].kind == QS_STEP_DENSE;
-    for (int e = 0; e < 48; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
+    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
   }
   for (uint32_t i = 0; i < QS_MAX_ITER; ++i) qs_build_io_tab(P, i, &io, QS_THREADS_LOG2);
   io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
@@ -45,7 +45,8 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
       if (P.steps[s].has_sign) zmask[s] = qs_step_zmask(P, s, base);
     if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io);
+      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io,
+                    [](qs_c128* dst, const qs_c128* src) { *dst = *src; });
     for (int s = 0; s < nsteps; ++s)
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
         // same variant selection as launch_pass() in kernels.cu

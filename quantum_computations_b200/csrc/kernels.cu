@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -70,11 +71,27 @@ int bind_device(const void* ptr, DevCtx** ctx) {
 // =====================================================================================
 // Tile pass: the fused multi-gate kernel (plan.h / tile_exec.h)
 // =====================================================================================
+// 16-byte asynchronous global->shared copy (LDGSTS): no register staging, and the
+// thread does not wait, so the next tile streams in while the current one computes.
+struct CopyAsync16 {
+  __device__ __forceinline__ void operator()(qs_c128* dst, const qs_c128* src) const {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+  }
+};
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One pass of the fused plan.  Persistent grid: every CTA loops over tiles.  With
+// `dbuf` the dynamic shared memory holds two tile buffers and the loads of tile
+// k+1 are issued before the steps of tile k run.
 template <int MAXR, bool DENSE>
 __global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
-k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
+k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
-  qs_c128* tile = reinterpret_cast<qs_c128*>(qs_smem);
+  qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
+  qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
   __shared__ QsStepTab s_tab[QS_MAX_STEPS];
   __shared__ QsIoTab s_io;
   __shared__ uint32_t s_zmask[QS_MAX_STEPS + 2];   // [nsteps], then final z, final g
@@ -82,8 +99,8 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
   const int nsteps = (int)P.nsteps;
 
   // tile-independent tables, once per launch (the grid is persistent)
-  for (int e = (int)tid; e < nsteps * 48; e += QS_THREADS)
-    qs_build_step_tab(P, e / 48, e % 48, &s_tab[e / 48], QS_THREADS_LOG2);
+  for (int e = (int)tid; e < nsteps * QS_TAB_ENTRIES; e += QS_THREADS)
+    qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
   if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
   if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
@@ -91,31 +108,56 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles) {
   const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   __syncthreads();
 
-  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  uint64_t t = blockIdx.x;
+  if (dbuf && t < ntiles)
+    qs_phase_load(P, state, buf0, qs_tile_base(P, t), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+  cp_async_commit();
+
+  for (uint32_t k = 0; t < ntiles; t += gridDim.x, ++k) {
+    qs_c128* cur = (dbuf && (k & 1u)) ? buf1 : buf0;
+    qs_c128* nxt = (k & 1u) ? buf0 : buf1;
     const uint64_t base = qs_tile_base(P, t);
     if ((int)tid < nsteps) {
       if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zmask(P, (int)tid, base);
     } else if ((int)tid == nsteps && P.fin_has_sign) {
       qs_fin_prepare(P, base, &s_zmask[nsteps], &s_zmask[nsteps + 1]);
     }
-    qs_phase_load(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_io);
+    if (dbuf) {
+      const uint64_t tn = t + gridDim.x;
+      if (tn < ntiles)
+        qs_phase_load(P, state, nxt, qs_tile_base(P, tn), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+      cp_async_commit();
+      cp_async_wait<1>();          // everything but the prefetch just issued has landed
+    } else {
+      qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncthreads();
     for (int s = 0; s < nsteps; ++s) {
-      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s]);
+      qs_phase_step_any<MAXR, DENSE>(P, s, cur, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s]);
       __syncthreads();
     }
-    qs_phase_store(P, state, tile, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
+    qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
                    s_zmask[nsteps + 1]);
     __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
-typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t);
+typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int);
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
   const uint64_t ntiles = 1ull << (n - (int)P.T);
-  const int smem = (int)(sizeof(qs_c128) << P.T);
+  // double-buffer when two tiles still leave room for three CTAs per SM (T <= 11);
+  // QSIM_DBUF=0/1 overrides for experiments
+  static const int dbuf_env = [] {
+    const char* e = getenv("QSIM_DBUF");
+    return e ? atoi(e) : -1;
+  }();
+  const int dbuf = dbuf_env >= 0 ? (dbuf_env != 0) : (P.T <= 11);
+  const int smem = (int)(sizeof(qs_c128) << P.T) * (dbuf ? 2 : 1);
   int maxr = 1;
   bool dense = false;
   for (uint32_t s = 0; s < P.nsteps; ++s) {
@@ -136,7 +178,7 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
   uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
   if (grid > ntiles) grid = ntiles;
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles);
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -48,12 +48,19 @@ enum QsStepKind : uint8_t {
   QS_STEP_DENSE = 1    // one 2^r x 2^r matrix on the r group bits
 };
 
+enum QsMatForm : uint8_t {
+  QS_FORM_GENERAL  = 0,
+  QS_FORM_DIAG     = 1,   // off-diagonal entries exactly zero
+  QS_FORM_ANTIDIAG = 2    // diagonal entries exactly zero (X-like)
+};
+
 struct QsStep {
   uint8_t  kind;
   uint8_t  r;                    // number of group bits
   uint8_t  gpos[QS_MAX_R];       // local position of matrix factor f (f=0: most significant)
   uint8_t  fpos[QS_MAX_T];       // the T-r free local positions, in thread-scatter order
   uint8_t  has_sign;             // 1 if the step's sign block is not empty
+  uint8_t  form[QS_MAX_R];       // QS_STEP_1Q: shape of each 2x2 (QsMatForm), saves flops
   uint16_t coef_off;             // first coefficient (in doubles) in QsPass::coef
   // sign block (only pairs touching a group bit)
   uint16_t pair_off;             // first (local position, outer global bit) pair in QsPass::pairs
@@ -91,6 +98,7 @@ struct QsStepTab {
   uint16_t jA[16];               // local-index bits of thread-id nibble 0
   uint16_t jB[16];               // local-index bits of thread-id nibble 1
   uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
+  uint16_t sdep[16];             // swizzled slot offset of amplitude m of a work item
 };
 
 // Tables for the load/store phases and the final sign block.

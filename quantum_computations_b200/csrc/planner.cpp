@@ -28,7 +28,7 @@ const char* last_error() { return g_error.c_str(); }
 qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   qsim_plan_options_t o{};
   if (opt) o = *opt;
-  if (o.tile_bits <= 0) o.tile_bits = 12;
+  if (o.tile_bits <= 0) o.tile_bits = 11;
   if (o.low_bits <= 0) o.low_bits = 4;
   if (o.max_group <= 0) o.max_group = 3;
   if (o.max_dense_ops <= 0) o.max_dense_ops = 16;
@@ -208,6 +208,14 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
 
 namespace {
 
+// shape of a 2x2 matrix: lets the kernel skip the multiplications by exact zeros
+uint8_t mat_form(const Op& op) {
+  auto zero = [](const cplx& v) { return v.real() == 0.0 && v.imag() == 0.0; };
+  if (zero(op.mat[1]) && zero(op.mat[2])) return QS_FORM_DIAG;
+  if (zero(op.mat[0]) && zero(op.mat[3])) return QS_FORM_ANTIDIAG;
+  return QS_FORM_GENERAL;
+}
+
 struct Walker {
   int n;
   const std::vector<Op>& ops;
@@ -332,6 +340,7 @@ struct Walker {
           if (pass) {
             QsStep& st = pass->steps[join];
             st.gpos[st.r] = (uint8_t)lpos[op.bits[0]];
+            st.form[st.r] = mat_form(op);
             double* dst = pass->coef + st.coef_off + 8 * st.r;
             for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
             st.r++;
@@ -348,6 +357,7 @@ struct Walker {
             st->kind = (op.k == 1) ? QS_STEP_1Q : QS_STEP_DENSE;
             st->r = (uint8_t)op.k;
             for (int f = 0; f < op.k; ++f) st->gpos[f] = (uint8_t)lpos[op.bits[f]];
+            if (op.k == 1) st->form[0] = mat_form(op);
             double* dst = pass->coef + ncoef;
             for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
           }

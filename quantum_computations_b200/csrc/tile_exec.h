@@ -72,7 +72,9 @@ QS_HD uint32_t qs_fin_neigh(const QsPass& P, uint32_t x) {
 }
 
 // ---- per-launch tables (tile independent) -----------------------------------------------
-// Entry e (0..47) of a step's table: 0..15 -> jA, 16..31 -> jB, 32..47 -> hi.
+// Entry e (0..63) of a step's table: 0..15 -> jA, 16..31 -> jB, 32..47 -> hi,
+// 48..63 -> sdep.
+#define QS_TAB_ENTRIES 64
 QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint32_t nthr_log2) {
   const QsStep& st = P.steps[s];
   const int nfree = (int)P.T - st.r;
@@ -83,9 +85,15 @@ QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint
   } else if (e < 32) {
     const int c = lo_bits - 4 < 0 ? 0 : (lo_bits - 4 > 4 ? 4 : lo_bits - 4);
     tab->jB[e - 16] = (uint16_t)qs_scatter8((uint32_t)(e - 16), st.fpos + 4, c);
-  } else {
+  } else if (e < 48) {
     const uint32_t jhi = qs_scatter8((uint32_t)(e - 32), st.fpos + nthr_log2, nfree - lo_bits);
     tab->hi[e - 32] = jhi | (qs_swz(jhi) << 16);
+  } else {
+    // amplitude m: matrix factor f is bit (r-1-f) of m and sits at local position gpos[f]
+    const int m = e - 48;
+    uint32_t d = 0;
+    for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
+    tab->sdep[m] = (uint16_t)qs_swz(d);
   }
 }
 
@@ -137,13 +145,16 @@ QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
 }
 
 // ---- phase: global -> shared ------------------------------------------------
+// `copy(dst, src)` moves one amplitude: a plain assignment on the host, a 16-byte
+// cp.async on the device (so the next tile streams in while this one computes).
+template <class Copy>
 QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, uint64_t base, uint32_t tid,
-                         uint32_t nthr_log2, uint64_t glo, const QsIoTab& io) {
+                         uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, Copy copy) {
   const uint32_t nthr = 1u << nthr_log2;
   const uint32_t size = 1u << P.T;
   const uint32_t slo = qs_swz(tid);
   const uint64_t b0 = base | glo;
-  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) tile[slo ^ io.shi[i]] = state[b0 | io.ghi[i]];
+  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) copy(tile + (slo ^ io.shi[i]), state + (b0 | io.ghi[i]));
 }
 
 // ---- phase: shared -> global, with the pass's final sign block ---------------
@@ -181,6 +192,22 @@ QS_HD void qs_mat2(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
   a1.y = m10r * y0 + m10i * x0 + m11r * y1 + m11i * x1;
 }
 
+// diagonal / antidiagonal 2x2: two complex multiplies instead of four
+QS_HD void qs_mat2_diag(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
+  const double x0 = a0.x, y0 = a0.y, x1 = a1.x, y1 = a1.y;
+  a0.x = m[0] * x0 - m[1] * y0;
+  a0.y = m[0] * y0 + m[1] * x0;
+  a1.x = m[6] * x1 - m[7] * y1;
+  a1.y = m[6] * y1 + m[7] * x1;
+}
+QS_HD void qs_mat2_anti(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
+  const double x0 = a0.x, y0 = a0.y, x1 = a1.x, y1 = a1.y;
+  a0.x = m[2] * x1 - m[3] * y1;
+  a0.y = m[2] * y1 + m[3] * x1;
+  a1.x = m[4] * x0 - m[5] * y0;
+  a1.y = m[4] * y0 + m[5] * x0;
+}
+
 // ---- phase: one step ------------------------------------------------------------
 // R group bits; every work item is the 2^R amplitudes that differ only in them.
 // Amplitude m of a work item has local index j0 ^ dep[m]; matrix factor f is bit
@@ -199,29 +226,31 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   uint32_t ng[R];                          // in-tile partners of group factor f
   uint32_t zg = 0;                         // Z on the group bits, in m-space
   uint32_t qg = 0;                         // bit m: pairs inside the group
-  {
+#pragma unroll
+  for (int m = 0; m < NA; ++m) sdep[m] = tab.sdep[m];
+  if (has_sign) {
     uint32_t gp[R];
 #pragma unroll
     for (int f = 0; f < R; ++f) {
       gp[f] = st.gpos[f];
-      ng[f] = has_sign ? (uint32_t)st.ng[f] : 0u;
+      ng[f] = (uint32_t)st.ng[f];
       zg |= ((zmask >> gp[f]) & 1u) << (R - 1 - f);
     }
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
-      uint32_t d = 0, q = 0;
+      uint32_t q = 0;
 #pragma unroll
-      for (int f = 0; f < R; ++f) {
+      for (int f = 0; f < R; ++f)
         if ((m >> (R - 1 - f)) & 1) {
-          d |= 1u << gp[f];
 #pragma unroll
           for (int f2 = f + 1; f2 < R; ++f2)
             if ((m >> (R - 1 - f2)) & 1) q ^= (ng[f] >> gp[f2]) & 1u;
         }
-      }
-      sdep[m] = qs_swz(d);
       qg |= q << m;
     }
+  } else {
+#pragma unroll
+    for (int f = 0; f < R; ++f) ng[f] = 0;
   }
 
   const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 15u];
@@ -255,9 +284,20 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
       for (int f = 0; f < R; ++f) {
         const double* mat = P.coef + st.coef_off + 8 * f;
         const int bit = 1 << (R - 1 - f);
+        const uint32_t form = st.form[f];
+        if (form == QS_FORM_GENERAL) {
 #pragma unroll
-        for (int m = 0; m < NA; ++m)
-          if (!(m & bit)) qs_mat2(mat, a[m], a[m | bit]);
+          for (int m = 0; m < NA; ++m)
+            if (!(m & bit)) qs_mat2(mat, a[m], a[m | bit]);
+        } else if (form == QS_FORM_DIAG) {
+#pragma unroll
+          for (int m = 0; m < NA; ++m)
+            if (!(m & bit)) qs_mat2_diag(mat, a[m], a[m | bit]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < NA; ++m)
+            if (!(m & bit)) qs_mat2_anti(mat, a[m], a[m | bit]);
+        }
       }
 #pragma unroll
       for (int m = 0; m < NA; ++m) tile[s0 ^ sdep[m]] = a[m];
@@ -274,11 +314,8 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           re += mr * a[c].x - mi * a[c].y;
           im += mr * a[c].y + mi * a[c].x;
         }
-        uint32_t d = 0;
-#pragma unroll
-        for (int f = 0; f < R; ++f) d |= (uint32_t)((row >> (R - 1 - f)) & 1) << st.gpos[f];
         qs_c128 o; o.x = re; o.y = im;
-        tile[s0 ^ qs_swz(d)] = o;
+        tile[s0 ^ tab.sdep[row]] = o;
       }
     }
   }
