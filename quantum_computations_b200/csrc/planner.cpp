@@ -251,44 +251,67 @@ struct Walker {
     uint8_t pend[256][2];
     int npend = 0;
 
-    // attach to the step being created (group = op bits) every pending pair that
-    // touches a group bit
-    auto attach_pairs = [&](QsStep* st, const Op& op, uint64_t gmask) {
-      int kept = 0, n_lo = 0;
+    // (local position, outer bit) pairs per step; flattened into QsPass::pairs at the end
+    constexpr int kMaxLo = 24;
+    uint8_t step_lo[QS_MAX_STEPS][kMaxLo][2];
+    int step_nlo[QS_MAX_STEPS];
+    int total_lo = 0;
+
+    // Earliest existing step that a matrix on bit c may join, given the pending
+    // pairs that touch c (they would be attached to that step's sign block, so the
+    // step must come after every earlier matrix on their partner bits).
+    auto earliest_step = [&](int c) {
+      int e = std::max(last_dense[c] + 1, last_sign[c]);
+      if (pend_mask >> c & 1)
+        for (int p = 0; p < npend; ++p) {
+          const int a = pend[p][0], b = pend[p][1];
+          if (a == c && b != c) e = std::max(e, last_dense[b] + 1);
+          else if (b == c && a != c) e = std::max(e, last_dense[a] + 1);
+        }
+      return e;
+    };
+    auto pending_lo_count = [&](int c) {
+      int cnt = 0;
+      if (pend_mask >> c & 1)
+        for (int p = 0; p < npend; ++p) {
+          const int a = pend[p][0], b = pend[p][1];
+          if ((a == c) != (b == c) && lpos[a == c ? b : a] < 0) ++cnt;
+        }
+      return cnt;
+    };
+    // Move every pending pair that touches bit c (factor f of step sidx) into that
+    // step's sign block.
+    auto attach = [&](int c, int sidx, int f, QsStep* st) {
+      if (!(pend_mask >> c & 1)) return;
+      int kept = 0;
       uint64_t new_mask = 0;
-      uint8_t* dst = pass ? pass->pairs + 2 * npairs : nullptr;
       for (int p = 0; p < npend; ++p) {
         const int a = pend[p][0], b = pend[p][1];
-        const bool ga = (gmask >> a) & 1, gb = (gmask >> b) & 1;
-        if (!ga && !gb) {
+        if (a != c && b != c) {
           pend[kept][0] = (uint8_t)a; pend[kept][1] = (uint8_t)b; ++kept;
           new_mask |= (1ull << a) | (1ull << b);
           continue;
         }
-        last_sign[a] = nsteps; last_sign[b] = nsteps;
-        const bool mixed = (lpos[a] < 0) != (lpos[b] < 0);
-        if (!st) {
-          if (mixed) ++n_lo;
-          continue;
+        const int e = (a == c) ? b : a;              // partner (== c for a Z)
+        last_sign[c] = std::max(last_sign[c], sidx);
+        last_sign[e] = std::max(last_sign[e], sidx);
+        if (e != c && lpos[e] < 0) {
+          step_lo[sidx][step_nlo[sidx]][0] = (uint8_t)lpos[c];
+          step_lo[sidx][step_nlo[sidx]][1] = (uint8_t)e;
+          step_nlo[sidx]++;
+          ++total_lo;
         }
+        if (!st) continue;
         st->has_sign = 1;
-        auto factor_of = [&](int bit) {
-          for (int f = 0; f < op.k; ++f)
-            if (op.bits[f] == bit) return f;
-          return 0;
-        };
-        if (a == b) {
-          st->zconst ^= (uint16_t)(1u << lpos[a]);
-        } else if (!mixed) {
-          if (ga) st->ng[factor_of(a)] ^= (uint16_t)(1u << lpos[b]);
-          if (gb) st->ng[factor_of(b)] ^= (uint16_t)(1u << lpos[a]);
-        } else {
-          const int in = ga ? a : b, outb = ga ? b : a;     // the group bit is inside the tile
-          dst[2 * n_lo] = (uint8_t)lpos[in]; dst[2 * n_lo + 1] = (uint8_t)outb; ++n_lo;
+        if (e == c) {
+          st->zconst ^= (uint16_t)(1u << lpos[c]);
+        } else if (lpos[e] >= 0) {
+          st->ng[f] ^= (uint16_t)(1u << lpos[e]);
+          // partner inside the same group (multi-qubit dense step): keep ng symmetric
+          for (int f2 = 0; f2 < st->r; ++f2)
+            if (f2 != f && st->gpos[f2] == lpos[e]) st->ng[f2] ^= (uint16_t)(1u << lpos[c]);
         }
       }
-      if (st) { st->pair_off = (uint16_t)npairs; st->n_lo = (uint16_t)n_lo; }
-      npairs += n_lo;
       npend = kept;
       pend_mask = new_mask;
     };
@@ -299,7 +322,7 @@ struct Walker {
       const Op& op = ops[i];
       const uint64_t m = masks[i];
       if (op.kind == OP_SIGN) {
-        const bool room = npairs + npend + 1 <= QS_MAX_PAIRS && npend < 250;
+        const bool room = total_lo + npend + 1 <= QS_MAX_PAIRS && npend < 250;
         if ((m & blocked_full) == 0 && room) {
           // CZ is an involution: a repeated pending pair cancels
           const int a = std::min(op.bits[0], op.bits[1]), b = std::max(op.bits[0], op.bits[1]);
@@ -325,32 +348,42 @@ struct Walker {
         bool take = in_tile && free_bits && op.k <= QS_MAX_R && dense_taken < opt.max_dense_ops;
         int join = -1;
         if (take) {
-          if (op.k == 1 && !(pend_mask & m)) {
+          if (op.k == 1) {
             const int c = op.bits[0];
-            const int earliest = std::max(last_dense[c] + 1, last_sign[c]);
-            for (int sidx = earliest; sidx < nsteps; ++sidx)
-              if (step_r[sidx] >= 1 && step_r[sidx] < opt.max_group) { join = sidx; break; }
+            const int nlo = pending_lo_count(c);
+            for (int sidx = earliest_step(c); sidx < nsteps; ++sidx)
+              if (step_r[sidx] >= 1 && step_r[sidx] < opt.max_group && step_nlo[sidx] + nlo <= kMaxLo) {
+                join = sidx;
+                break;
+              }
           }
           if (join < 0) {
             const int need = (op.k == 1) ? 8 * opt.max_group : 2 * (1 << op.k) * (1 << op.k);
-            if (nsteps >= QS_MAX_STEPS || ncoef + need > QS_MAX_COEF) take = false;
+            int nlo = 0;
+            for (int b : op.bits) nlo += pending_lo_count(b);
+            if (nsteps >= QS_MAX_STEPS || ncoef + need > QS_MAX_COEF || nlo > kMaxLo ||
+                total_lo + nlo + npend > QS_MAX_PAIRS)
+              take = false;
           }
         }
         if (take && join >= 0) {
-          if (pass) {
-            QsStep& st = pass->steps[join];
-            st.gpos[st.r] = (uint8_t)lpos[op.bits[0]];
-            st.form[st.r] = mat_form(op);
-            double* dst = pass->coef + st.coef_off + 8 * st.r;
+          const int c = op.bits[0];
+          const int f = step_r[join];
+          QsStep* st = pass ? &pass->steps[join] : nullptr;
+          if (st) {
+            st->gpos[f] = (uint8_t)lpos[c];
+            st->form[f] = mat_form(op);
+            double* dst = pass->coef + st->coef_off + 8 * f;
             for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
-            st.r++;
+            st->r++;
           }
+          attach(c, join, f, st);
           step_r[join]++;
-          last_dense[op.bits[0]] = join;
+          last_dense[c] = join;
         } else if (take) {
           QsStep* st = pass ? &pass->steps[nsteps] : nullptr;
           if (st) *st = QsStep{};
-          attach_pairs(st, op, m);
+          step_nlo[nsteps] = 0;
           const int dim = 1 << op.k;
           if (st) {
             st->coef_off = (uint16_t)ncoef;
@@ -361,6 +394,7 @@ struct Walker {
             double* dst = pass->coef + ncoef;
             for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
           }
+          for (int f = 0; f < op.k; ++f) attach(op.bits[f], nsteps, f, st);
           if (op.k == 1) {
             ncoef += 8 * opt.max_group;       // room for later members of the group
             step_r[nsteps] = 1;
@@ -384,6 +418,17 @@ struct Walker {
     }
 
     if (pass) {
+      // flatten the per-step (local, outer) pair lists
+      for (int sidx = 0; sidx < nsteps; ++sidx) {
+        QsStep& st = pass->steps[sidx];
+        st.pair_off = (uint16_t)npairs;
+        st.n_lo = (uint16_t)step_nlo[sidx];
+        for (int q = 0; q < step_nlo[sidx]; ++q) {
+          pass->pairs[2 * npairs] = step_lo[sidx][q][0];
+          pass->pairs[2 * npairs + 1] = step_lo[sidx][q][1];
+          ++npairs;
+        }
+      }
       // whatever is still pending goes into the final block
       uint8_t* dst = pass->pairs + 2 * npairs;
       int w = 0, n_oo = 0, n_lo = 0;
