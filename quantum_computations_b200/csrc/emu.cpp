@@ -32,6 +32,7 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   }
   for (uint32_t i = 0; i < QS_MAX_ITER; ++i) qs_build_io_tab(P, i, &io, QS_THREADS_LOG2);
   io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  for (uint32_t e = 0; e < 256; ++e) qs_build_base_tab(P, e, &io);
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
   std::vector<uint64_t> glo(QS_THREADS);
   std::vector<uint32_t> fin_qlo(QS_THREADS);
@@ -40,7 +41,7 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
     fin_qlo[tid] = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   }
   for (uint64_t t = 0; t < ntiles; ++t) {
-    const uint64_t base = qs_tile_base(P, t);
+    const uint64_t base = qs_tile_base_tab(P, io, t);
     for (int s = 0; s < nsteps; ++s)
       if (P.steps[s].has_sign) zmask[s] = qs_step_zmask(P, s, base);
     if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);

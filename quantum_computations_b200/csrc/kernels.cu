@@ -27,6 +27,7 @@ struct DevCtx {
   double* d_partials = nullptr;   // [kReduceBlocks][2]
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
+  unsigned* d_sm_arrival = nullptr;  // [256] CTA arrival counters per SM (never reset: used mod occupancy)
   int occ[4] = {0, 0, 0, 0};      // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
@@ -62,6 +63,8 @@ int bind_device(const void* ptr, DevCtx** ctx) {
     QS_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks));
     QS_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 2));
     QS_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 2));
+    QS_CUDA(cudaMalloc(&c.d_sm_arrival, sizeof(unsigned) * 256));
+    QS_CUDA(cudaMemset(c.d_sm_arrival, 0, sizeof(unsigned) * 256));
     c.ready = true;
   }
   *ctx = &c;
@@ -88,7 +91,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // k+1 are issued before the steps of tile k run.
 template <int MAXR, bool DENSE>
 __global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
-k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf) {
+k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf,
+            unsigned* sm_arrival, int stagger_cycles, int occ) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
   qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
@@ -103,20 +107,37 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
   if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
   if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  qs_build_base_tab(P, tid, &s_io);          // QS_THREADS == 256 entries
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
   const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
   const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   __syncthreads();
 
+  // The CTAs that share an SM all run the same load / compute / store cycle; started
+  // together they stay in lockstep (all loading, then all computing) and HBM and the
+  // FP64 pipe take turns idling.  Offset them by a fraction of the cycle instead.
+  if (stagger_cycles > 0) {
+    __shared__ unsigned s_rank;
+    if (tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_rank = atomicAdd(&sm_arrival[smid & 255u], 1u) % (unsigned)occ;
+    }
+    __syncthreads();
+    const long long wait = (long long)s_rank * stagger_cycles;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) __nanosleep(200);
+  }
+
   uint64_t t = blockIdx.x;
   if (dbuf && t < ntiles)
-    qs_phase_load(P, state, buf0, qs_tile_base(P, t), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+    qs_phase_load(P, state, buf0, qs_tile_base_tab(P, s_io, t), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
   cp_async_commit();
 
   for (uint32_t k = 0; t < ntiles; t += gridDim.x, ++k) {
     qs_c128* cur = (dbuf && (k & 1u)) ? buf1 : buf0;
     qs_c128* nxt = (k & 1u) ? buf0 : buf1;
-    const uint64_t base = qs_tile_base(P, t);
+    const uint64_t base = qs_tile_base_tab(P, s_io, t);
     if ((int)tid < nsteps) {
       if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zmask(P, (int)tid, base);
     } else if ((int)tid == nsteps && P.fin_has_sign) {
@@ -125,7 +146,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     if (dbuf) {
       const uint64_t tn = t + gridDim.x;
       if (tn < ntiles)
-        qs_phase_load(P, state, nxt, qs_tile_base(P, tn), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+        qs_phase_load(P, state, nxt, qs_tile_base_tab(P, s_io, tn), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
       cp_async_commit();
       cp_async_wait<1>();          // everything but the prefetch just issued has landed
     } else {
@@ -145,7 +166,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
   cp_async_wait<0>();
 }
 
-typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int);
+typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, unsigned*, int, int);
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
@@ -178,7 +199,26 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
   uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
   if (grid > ntiles) grid = ntiles;
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf);
+  // stagger the co-resident CTAs by 1/occ of the estimated per-tile time
+  // (memory at ~18 B/clk/SM, FP64 at 64 FMA/clk/SM); QSIM_STAGGER=0 disables
+  static const int stagger_env = [] {
+    const char* e = getenv("QSIM_STAGGER");
+    return e ? atoi(e) : -1;
+  }();
+  int stagger = 0;
+  if (occ > 1 && ntiles >= grid * 4 && stagger_env != 0) {
+    double dp_per_amp = 0.0;
+    for (uint32_t s = 0; s < P.nsteps; ++s) {
+      const QsStep& st = P.steps[s];
+      if (st.kind == QS_STEP_DENSE) dp_per_amp += 4.0 * (1 << st.r);
+      else
+        for (int f = 0; f < st.r; ++f) dp_per_amp += st.form[f] == QS_FORM_GENERAL ? 8.0 : 4.0;
+    }
+    const double amps = (double)(1u << P.T);
+    const double cycles = amps * 32.0 / 18.0 + amps * dp_per_amp / 64.0;
+    stagger = stagger_env > 0 ? stagger_env : (int)(cycles / occ);
+  }
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, ctx->d_sm_arrival, stagger, occ);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -36,7 +36,7 @@
 
 #define QS_MAX_T        13     // largest tile: 2^13 amplitudes = 128 KiB
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
-#define QS_MAX_STEPS    48
+#define QS_MAX_STEPS    40
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #define QS_THREADS_LOG2 8
@@ -107,4 +107,5 @@ struct QsIoTab {
   uint16_t shi[QS_MAX_ITER];     // swz(i << QS_THREADS_LOG2)
   uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
   uint32_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
+  uint64_t base_tab[4][64];      // tile number -> global index of the tile, 6 bits at a time
 };

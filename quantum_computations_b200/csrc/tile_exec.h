@@ -58,6 +58,16 @@ QS_HD uint64_t qs_tile_base(const QsPass& P, uint64_t tile) {
   return base;
 }
 
+// The same through the per-launch table (the deposit is OR-linear in the tile
+// number): four lookups instead of a T-step loop.  Tile numbers beyond 24 bits
+// fall back to the loop for the excess.
+QS_HD uint64_t qs_tile_base_tab(const QsPass& P, const QsIoTab& io, uint64_t tile) {
+  uint64_t base = io.base_tab[0][tile & 63u] | io.base_tab[1][(tile >> 6) & 63u] |
+                  io.base_tab[2][(tile >> 12) & 63u] | io.base_tab[3][(tile >> 18) & 63u];
+  if (tile >> 24) base |= qs_tile_base(P, (tile >> 24) << 24);
+  return base;
+}
+
 // Q(x) of the final block: every coupled pair inside x counted once.
 QS_HD uint32_t qs_fin_quad(const QsPass& P, uint32_t x) {
   uint32_t q = 0;
@@ -103,6 +113,9 @@ QS_HD void qs_build_io_tab(const QsPass& P, uint32_t i, QsIoTab* io, uint32_t nt
   io->shi[i] = (uint16_t)qs_swz(jhi & ((1u << P.T) - 1u));
   io->fin_neigh[i] = 0;
   if (P.fin_has_sign && jhi < (1u << P.T)) io->fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
+}
+QS_HD void qs_build_base_tab(const QsPass& P, uint32_t e, QsIoTab* io) {   // e in [0, 256)
+  io->base_tab[e >> 6][e & 63u] = qs_tile_base(P, (uint64_t)(e & 63u) << (6 * (e >> 6)));
 }
 // fin_q is a bit mask over i; build it with one thread (or sequentially on the host)
 QS_HD uint32_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
