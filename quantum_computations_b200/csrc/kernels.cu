@@ -92,7 +92,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int MAXR, bool DENSE>
 __global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf,
-            unsigned* sm_arrival, int stagger_cycles, int occ) {
+            unsigned* sm_arrival, int stagger_cycles, int occ, int debug_skip) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
   qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
@@ -150,7 +150,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
       cp_async_commit();
       cp_async_wait<1>();          // everything but the prefetch just issued has landed
     } else {
-      qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
+      if (!(debug_skip & 1)) qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
       cp_async_commit();
       cp_async_wait<0>();
     }
@@ -159,14 +159,15 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
       qs_phase_step_any<MAXR, DENSE>(P, s, cur, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s]);
       __syncthreads();
     }
-    qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
-                   s_zmask[nsteps + 1]);
+    if (!(debug_skip & 2))
+      qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
+                     s_zmask[nsteps + 1]);
     __syncthreads();
   }
   cp_async_wait<0>();
 }
 
-typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, unsigned*, int, int);
+typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, unsigned*, int, int, int);
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
@@ -218,7 +219,14 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
     const double cycles = amps * 32.0 / 18.0 + amps * dp_per_amp / 64.0;
     stagger = stagger_env > 0 ? stagger_env : (int)(cycles / occ);
   }
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, ctx->d_sm_arrival, stagger, occ);
+  // QSIM_DEBUG_SKIP (development only): bit 0 skips the global loads, bit 1 the global
+  // stores of a pass, to time the shared-memory/FP64 part on its own (results are garbage)
+  static const int debug_skip = [] {
+    const char* e = getenv("QSIM_DEBUG_SKIP");
+    return e ? atoi(e) : 0;
+  }();
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, ctx->d_sm_arrival, stagger, occ,
+                                                          debug_skip);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -12,7 +12,7 @@
 #define QS_HD inline
 #endif
 
-struct qs_c128 { double x, y; };   // layout-compatible with double2 / complex128
+struct alignas(16) qs_c128 { double x, y; };   // complex128; 16-byte aligned so every access is one 128-bit op
 
 QS_HD uint32_t qs_par(uint32_t v) {
 #if defined(__CUDA_ARCH__)
