@@ -61,6 +61,10 @@ static bool is_z(const std::vector<cplx>& m) {
   return is_diagonal(m, 2) && is_exact(m[0], 1.0) && is_exact(m[3], -1.0);
 }
 
+static bool is_antidiagonal(const std::vector<cplx>& m) {   // 2x2 only
+  return m[0].real() == 0.0 && m[0].imag() == 0.0 && m[3].real() == 0.0 && m[3].imag() == 0.0;
+}
+
 static bool is_identity(const std::vector<cplx>& m, int dim) {
   if (!is_diagonal(m, dim)) return false;
   for (int r = 0; r < dim; ++r)
@@ -168,12 +172,38 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
       continue;
     }
     if (g.kind == OP_SIGN) {
-      for (int b : g.bits) {
-        BitTrack& t = tr[b];
-        if (t.has_pending && !t.pending_diag) emit_pending(b);   // diagonal pendings slide through
-        if (t.since == SINCE_NOTHING) t.since = SINCE_DIAG;
+      const int a = g.bits[0], b = g.bits[1];
+      // Pending products that are diagonal slide through a CZ/Z unchanged.  Pending
+      // ANTIDIAGONAL products (X times a diagonal) slide through as well, leaving
+      // Pauli-frame debris behind:  CZ_ab P_a = P_a CZ_ab Z_b  and  Z_a P_a = -P_a Z_a.
+      // So bit flips never cost a pass of their own: they ride along until the next
+      // non-diagonal gate on the qubit absorbs them.
+      for (int x : g.bits) {
+        BitTrack& t = tr[x];
+        if (t.has_pending && !t.pending_diag && !is_antidiagonal(t.pending)) emit_pending(x);
       }
+      const bool anti_a = tr[a].has_pending && !tr[a].pending_diag;
+      const bool anti_b = tr[b].has_pending && !tr[b].pending_diag;
+      for (int x : g.bits)
+        if (tr[x].since == SINCE_NOTHING) tr[x].since = SINCE_DIAG;
       out.push_back(g);
+      auto emit_z = [&](int x) {
+        Op z;
+        z.kind = OP_SIGN;
+        z.k = 2;
+        z.bits = {x, x};
+        z.diag = true;
+        out.push_back(z);
+      };
+      if (a == b) {
+        if (anti_a)
+          for (cplx& v : tr[a].pending) v = -v;
+      } else {
+        if (anti_a) emit_z(b);
+        if (anti_b) emit_z(a);
+        if (anti_a && anti_b)
+          for (cplx& v : tr[a].pending) v = -v;
+      }
       continue;
     }
     // multi-qubit dense gate: swallow pending single-qubit gates on its qubits
