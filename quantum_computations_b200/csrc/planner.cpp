@@ -28,7 +28,7 @@ const char* last_error() { return g_error.c_str(); }
 qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   qsim_plan_options_t o{};
   if (opt) o = *opt;
-  if (o.tile_bits <= 0) o.tile_bits = 11;
+  if (o.tile_bits <= 0) o.tile_bits = 12;
   if (o.low_bits <= 0) o.low_bits = 4;
   if (o.max_group <= 0) o.max_group = 3;
   if (o.max_dense_ops <= 0) o.max_dense_ops = 16;
