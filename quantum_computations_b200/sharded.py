@@ -1,0 +1,282 @@
+"""State vectors larger than one GPU: shard by the top qubits, swap on demand.
+
+The reference has no distributed path at all; this module
+is what ``BASELINE.json`` configuration C5 (34 qubits over 8 B200s) needs.
+
+Layout.  A register of ``n`` qubits over ``P = 2^g`` ranks: rank ``r`` holds the
+``2^(n-g)`` amplitudes whose top ``g`` index bits equal ``r``.  The *physical*
+index bits ``0 .. n-g-1`` are local, bits ``n-g .. n-1`` are the rank number.
+A table maps every logical index bit (reference qubit ``q`` is logical bit
+``n-1-q``) to the physical bit it currently occupies.
+
+Execution.  Gates are consumed in program order:
+
+* a gate whose non-diagonal action touches only local bits joins the current
+  local segment, which is run by the single-GPU fused planner on the shard;
+* diagonal gates (Z, RZ, P, T, CZ, ...) never need communication: for the bits
+  that live in the rank number the diagonal is restricted to this rank's values
+  and becomes a smaller diagonal gate (or a scalar) on the shard;
+* a non-diagonal gate on a rank bit triggers a *global<->local swap*: that bit
+  changes places with the local bit whose next non-diagonal use lies farthest in
+  the future.  Every rank keeps the half of its shard that already agrees with
+  its rank bit and exchanges the other half with the partner rank
+  ``r ^ 2^(bit)`` -- one send and one receive of half a shard per rank, all
+  ``P/2`` pairs at once over NVLink/NVSwitch (``torch.distributed`` P2P on
+  NCCL).  When the local bit is the top local bit the halves are contiguous and
+  travel without staging; otherwise ``qsim_swap_pack`` / ``qsim_swap_unpack``
+  gather and scatter them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, engine
+
+
+def _is_diagonal(m: np.ndarray) -> bool:
+    return not np.any(m - np.diag(np.diagonal(m)))
+
+
+class Comm:
+    """Thin wrapper over ``torch.distributed`` point-to-point exchange of
+    complex128 buffers (moved as float64 pairs so gloo works too)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        if self.size & (self.size - 1):
+            raise ValueError("the number of ranks must be a power of two")
+        self.bytes_exchanged = 0
+
+    def exchange(self, send_t, recv_t, partner: int) -> None:
+        """Send ``send_t`` to and receive ``recv_t`` from ``partner`` (torch tensors)."""
+        import torch
+        dist = self.dist
+        s = torch.view_as_real(send_t) if send_t.is_complex() else send_t
+        r = torch.view_as_real(recv_t) if recv_t.is_complex() else recv_t
+        ops = [dist.P2POp(dist.isend, s, partner, self.group), dist.P2POp(dist.irecv, r, partner, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.bytes_exchanged += s.numel() * s.element_size()
+
+    def allreduce_sum(self, values: np.ndarray) -> np.ndarray:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64))
+        dev = getattr(self, "device", None)
+        if dev is not None:
+            t = t.to(dev)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+
+class ShardedState:
+    """One rank's shard plus the logical->physical bit table (same on all ranks)."""
+
+    def __init__(self, n: int, comm: Comm, backend=None, as_torch=None):
+        self.n = int(n)
+        self.comm = comm
+        self.g = comm.size.bit_length() - 1
+        if self.g >= self.n:
+            raise ValueError("more ranks than amplitudes")
+        self.n_local = self.n - self.g
+        self.backend = backend or engine.get_backend()
+        self.phys = list(range(self.n))           # phys[logical bit] = physical bit
+        self.buf = self.backend.empty(1 << self.n_local)
+        self.swaps = 0
+        self.swap_seconds = 0.0
+        # how to view a backend buffer as a torch tensor for the communicator
+        self._as_torch = as_torch or (lambda b: b)
+
+    # -- initial states ---------------------------------------------------------------------
+    def set_product(self, vectors) -> None:
+        """|psi> = kron of single-qubit kets (qubit 0 first).  The rank bits select
+        one amplitude of each of the first g kets: a scalar on this rank."""
+        vecs = [np.asarray(v, dtype=np.complex128) for v in vectors]
+        assert len(vecs) == self.n
+        self.phys = list(range(self.n))
+        scale = 1.0 + 0.0j
+        for q in range(self.g):                    # reference qubit q = logical bit n-1-q = rank bit
+            bit = (self.comm.rank >> (self.g - 1 - q)) & 1
+            scale *= vecs[q][bit]
+        local = [v.copy() for v in vecs[self.g:]]
+        local[0] = local[0] * scale
+        amps = np.ascontiguousarray(np.stack(local))
+        be = self.backend
+        _capi.check(be.lib, be.lib.qsim_init_product(
+            be.ptr(self.buf), self.n_local, amps.view(np.float64).ctypes.data_as(_capi.c_double_p), be.stream()))
+
+    # -- reductions ---------------------------------------------------------------------------
+    def norm(self) -> float:
+        be = self.backend
+        out = np.zeros(2)
+        _capi.check(be.lib, be.lib.qsim_reduce_norm2(be.ptr(self.buf), C.c_uint64(1 << self.n_local),
+                                                     out.ctypes.data_as(_capi.c_double_p), be.stream()))
+        return float(np.sqrt(self.comm.allreduce_sum(out[:1])[0]))
+
+    # -- swaps -----------------------------------------------------------------------------------
+    def swap(self, global_phys: int, local_phys: int) -> None:
+        """Exchange physical rank bit ``global_phys`` with physical local bit ``local_phys``."""
+        import time
+        be, lib = self.backend, self.backend.lib
+        gi = global_phys - self.n_local            # bit of the rank number
+        keep = (self.comm.rank >> gi) & 1
+        partner = self.comm.rank ^ (1 << gi)
+        half = 1 << (self.n_local - 1)
+        be.synchronize()                           # so the timer below sees the swap alone
+        t0 = time.perf_counter()
+        if local_phys == self.n_local - 1:
+            # halves are contiguous: send the half with top bit != keep, receive into it
+            lo = (1 - keep) * half
+            view = self._as_torch(self.buf)[lo:lo + half]
+            recv = self._as_torch(be.empty(half))
+            self.comm.exchange(view, recv, partner)
+            view.copy_(recv)
+        else:
+            send, recv = be.empty(half), be.empty(half)
+            qubit = self.n_local - 1 - local_phys  # local reference-style qubit number
+            _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), be.ptr(send), self.n_local, qubit, keep,
+                                                be.stream()))
+            self.comm.exchange(self._as_torch(send), self._as_torch(recv), partner)
+            _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), be.ptr(recv), self.n_local, qubit, keep,
+                                                  be.stream()))
+        be.synchronize()
+        self.swap_seconds += time.perf_counter() - t0
+        self.swaps += 1
+        # the two logical bits trade places
+        la, lb = self.phys.index(global_phys), self.phys.index(local_phys)
+        self.phys[la], self.phys[lb] = local_phys, global_phys
+
+    # -- gathering (tests / small registers only) -----------------------------------------------------
+    def gather_numpy(self) -> np.ndarray:
+        """Full state in logical order on every rank."""
+        import torch
+        local = torch.view_as_real(self._as_torch(self.buf)).contiguous()
+        parts = [torch.empty_like(local) for _ in range(self.comm.size)]
+        self.comm.dist.all_gather(parts, local, group=self.comm.group)
+        full = np.concatenate([torch.view_as_complex(p).cpu().numpy() for p in parts])   # physical order
+        # physical index -> logical index: move physical bit phys[l] to logical bit l
+        cube = full.reshape((2,) * self.n)                    # axis a <-> physical bit n-1-a
+        axes = [self.n - 1 - self.phys[self.n - 1 - a] for a in range(self.n)]   # logical axis a takes that physical axis
+        return np.ascontiguousarray(cube.transpose(axes)).reshape(-1)
+
+
+class ShardedSimulator:
+    """Runs a list of matrix gates (this package's ``Gate`` objects) on a ShardedState."""
+
+    def __init__(self, circuit, state: ShardedState, plan_options=None):
+        self.circuit = circuit
+        self.state = state
+        self.plan_options = plan_options
+        self.stats = {"segments": 0, "passes": 0, "swaps": 0, "local_gates": 0}
+
+    # ---- scheduling helpers ---------------------------------------------------------------------
+    def _lower(self):
+        """[(logical_bits (factor order), matrix, is_diag)]"""
+        n = self.state.n
+        out = []
+        for gate in self.circuit:
+            for targets, matrix in gate.lowered(n, False):
+                m = np.asarray(matrix, dtype=np.complex128)
+                out.append(([n - 1 - q for q in targets], m, _is_diagonal(m)))
+        return out
+
+    def _restrict_diagonal(self, bits_phys, matrix):
+        """Diagonal gate with some targets in the rank number: keep this rank's entries."""
+        st = self.state
+        k = len(bits_phys)
+        diag = np.diagonal(matrix).reshape((2,) * k)
+        index, local_bits = [], []
+        for f, p in enumerate(bits_phys):
+            if p >= st.n_local:
+                index.append((st.comm.rank >> (p - st.n_local)) & 1)
+            else:
+                index.append(slice(None))
+                local_bits.append(p)
+        sub = np.asarray(diag[tuple(index)]).reshape(-1)
+        if not local_bits:                           # pure scalar: put it on local bit 0
+            return [0], np.diag([sub[0], sub[0]])
+        return local_bits, np.diag(sub)
+
+    def compile(self):
+        """Walk the circuit once, tracking where every logical bit lives, and build
+        the schedule: fused local plans separated by global<->local swaps.  The
+        schedule starts from the identity layout (``set_product``)."""
+        st = self.state
+        ops = self._lower()
+        nloc = st.n_local
+        phys = list(range(st.n))                      # simulated layout
+        uses = {}
+        for idx, (bits, _m, is_diag) in enumerate(ops):
+            if not is_diag:
+                for b in bits:
+                    uses.setdefault(b, []).append(idx)
+        cursor = {b: 0 for b in uses}
+
+        def next_use(bit, now):
+            lst = uses.get(bit)
+            if not lst:
+                return 1 << 60
+            c = cursor[bit]
+            while c < len(lst) and lst[c] < now:
+                c += 1
+            cursor[bit] = c
+            return lst[c] if c < len(lst) else 1 << 60
+
+        schedule, segment = [], []
+
+        def flush():
+            if not segment:
+                return
+            plan = engine.Plan(st.backend, nloc, list(segment), self.plan_options)
+            schedule.append(("plan", plan))
+            self.stats["segments"] += 1
+            self.stats["passes"] += plan.stats["n_passes"]
+            self.stats["local_gates"] += len(segment)
+            segment.clear()
+
+        saved = st.phys
+        try:
+            for idx, (bits, m, is_diag) in enumerate(ops):
+                st.phys = phys                         # _restrict_diagonal reads the layout
+                p_bits = [phys[b] for b in bits]
+                if is_diag:
+                    if any(p >= nloc for p in p_bits):
+                        p_bits, m = self._restrict_diagonal(p_bits, m)
+                    segment.append(([nloc - 1 - p for p in p_bits], m))
+                    continue
+                for b in bits:
+                    if phys[b] < nloc:
+                        continue
+                    # bring logical bit b into the shard: evict the local bit needed latest
+                    flush()
+                    local_logical = [l for l in range(st.n) if phys[l] < nloc and l not in bits]
+                    victim = max(local_logical, key=lambda l: (next_use(l, idx), phys[l]))
+                    schedule.append(("swap", phys[b], phys[victim]))
+                    phys[b], phys[victim] = phys[victim], phys[b]
+                    self.stats["swaps"] += 1
+                segment.append(([nloc - 1 - phys[b] for b in bits], m))
+            flush()
+        finally:
+            st.phys = saved
+        self._schedule = schedule
+        return schedule
+
+    def run(self) -> ShardedState:
+        """Execute the schedule on the state (which must be in the identity layout,
+        e.g. right after ``set_product``)."""
+        st = self.state
+        if getattr(self, "_schedule", None) is None:
+            self.compile()
+        if st.phys != list(range(st.n)):
+            raise ValueError("the schedule assumes the identity layout; call set_product first")
+        for item in self._schedule:
+            if item[0] == "plan":
+                item[1].execute(st.buf)
+            else:
+                st.swap(item[1], item[2])
+        return st
