@@ -2,7 +2,7 @@
 
 ``declare(lib)`` attaches argument/return types to a loaded library.  The
 product binds ``csrc/libqsim_b200.so`` through ``engine.py``; the CPU tests bind
-the host emulator (same ABI, host pointers) through ``tests/emu_backend.py``.
+the host emulator (same ABI, host pointers) through a backend class of their own.
 """
 from __future__ import annotations
 
