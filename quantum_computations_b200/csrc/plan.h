@@ -39,7 +39,9 @@
 #define QS_MAX_STEPS    40
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
-#define QS_THREADS_LOG2 8
+#ifndef QS_THREADS_LOG2
+#define QS_THREADS_LOG2 8      // threads per CTA = 256 (9 = 512 is an experiment switch)
+#endif
 #define QS_THREADS      (1 << QS_THREADS_LOG2)
 #define QS_MAX_ITER     (1 << (QS_MAX_T - QS_THREADS_LOG2))   // amplitudes per thread in load/store
 
@@ -51,7 +53,12 @@ enum QsStepKind : uint8_t {
 enum QsMatForm : uint8_t {
   QS_FORM_GENERAL  = 0,
   QS_FORM_DIAG     = 1,   // off-diagonal entries exactly zero
-  QS_FORM_ANTIDIAG = 2    // diagonal entries exactly zero (X-like)
+  QS_FORM_ANTIDIAG = 2,   // diagonal entries exactly zero (X-like)
+  // unitary written as (real rotation [[c,-s],[s,c]]) x (diagonal phases): the
+  // phases of all factors of a step are applied as ONE table over the group bits
+  // (QsStep::ph_off), the rotation costs half the flops of a complex 2x2.
+  // Coefficient slot: c, s, then unused.
+  QS_FORM_ROT      = 3
 };
 
 struct QsStep {
@@ -61,6 +68,9 @@ struct QsStep {
   uint8_t  fpos[QS_MAX_T];       // the T-r free local positions, in thread-scatter order
   uint8_t  has_sign;             // 1 if the step's sign block is not empty
   uint8_t  form[QS_MAX_R];       // QS_STEP_1Q: shape of each 2x2 (QsMatForm), saves flops
+  uint8_t  has_phase;            // 1 if a phase table (2^r complex, indexed by m) precedes the matrices
+  uint8_t  pad0;
+  uint16_t ph_off;               // its offset (in doubles) in QsPass::coef
   uint16_t coef_off;             // first coefficient (in doubles) in QsPass::coef
   // sign block (only pairs touching a group bit)
   uint16_t pair_off;             // first (local position, outer global bit) pair in QsPass::pairs
@@ -96,7 +106,7 @@ static_assert(sizeof(QsPass) <= 32000, "QsPass must fit in the kernel parameter 
 // counter land inside the tile.
 struct QsStepTab {
   uint16_t jA[16];               // local-index bits of thread-id nibble 0
-  uint16_t jB[16];               // local-index bits of thread-id nibble 1
+  uint16_t jB[32];               // local-index bits of thread-id bits 4..8
   uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
   uint16_t sdep[16];             // swizzled slot offset of amplitude m of a work item
 };

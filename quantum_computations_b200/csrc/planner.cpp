@@ -72,6 +72,24 @@ static bool is_identity(const std::vector<cplx>& m, int dim) {
   return true;
 }
 
+// U = diag(l0, l1) . [[c, -s], [s, c]] . diag(1, r1)  for a 2x2 unitary with no zero
+// entry; returns false (and leaves the outputs alone) when U is not of that form to
+// within rounding, e.g. a non-unitary user matrix.
+static bool factor_rotation(const std::vector<cplx>& u, cplx& l0, cplx& l1, double& c, double& s, cplx& r1) {
+  const double c0 = std::abs(u[0]), s0 = std::abs(u[2]);
+  if (!(c0 > 1e-8) || !(s0 > 1e-8)) return false;
+  const cplx tl0 = u[0] / c0, tl1 = u[2] / s0;
+  const cplx tr1 = u[3] / (c0 * tl1);
+  // reconstruct and compare
+  const cplx v01 = -tl0 * s0 * tr1, v11 = tl1 * c0 * tr1;
+  const double scale = std::max(std::max(std::abs(u[0]), std::abs(u[1])), std::max(std::abs(u[2]), std::abs(u[3])));
+  const double err = std::max(std::abs(v01 - u[1]), std::abs(v11 - u[3]));
+  if (!(err <= 4e-15 * scale)) return false;
+  if (std::abs(std::abs(tr1) - 1.0) > 1e-13 || std::abs(std::abs(tl0) - 1.0) > 1e-13) return false;
+  l0 = tl0; l1 = tl1; c = c0; s = s0; r1 = tr1;
+  return true;
+}
+
 // 2x2 product a*b
 static std::vector<cplx> mul2(const std::vector<cplx>& a, const std::vector<cplx>& b) {
   std::vector<cplx> o(4);
@@ -94,6 +112,7 @@ static void fold_left(Op& op, int f, const std::vector<cplx>& g) {
   }
   op.mat.swap(o);
   op.diag = is_diagonal(op.mat, dim);
+  op.rot = false;
 }
 
 // m * (g on factor f)   -- g applied BEFORE m
@@ -149,6 +168,18 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
     o.bits = {b};
     o.mat = t.pending;
     o.diag = t.pending_diag;
+    // A general unitary leaves as (rotation . right phases); its left phases stay
+    // behind as a new pending diagonal that slides on to the next gate of the qubit.
+    cplx l0, l1, r1;
+    double c, s;
+    if (!o.diag && !is_antidiagonal(o.mat) && factor_rotation(o.mat, l0, l1, c, s, r1)) {
+      o.rot = true;
+      o.c = c; o.s = s; o.r0 = cplx(1.0, 0.0); o.r1 = r1;
+      o.mat = {cplx(c, 0.0), -s * r1, cplx(s, 0.0), c * r1};
+      t.has_pending = true;
+      t.pending = {l0, cplx(0.0, 0.0), cplx(0.0, 0.0), l1};
+      t.pending_diag = true;
+    }
     out.push_back(o);
     t.last_op = (int)out.size() - 1;
     t.last_factor = 0;
@@ -230,7 +261,10 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
       }
     }
   }
-  for (int b = 0; b < n; ++b) emit_pending(b);
+  for (int b = 0; b < n; ++b) {
+    emit_pending(b);        // a general gate leaves its left phases pending ...
+    emit_pending(b);        // ... which go out as a diagonal gate
+  }
   return out;
 }
 
@@ -240,10 +274,23 @@ namespace {
 
 // shape of a 2x2 matrix: lets the kernel skip the multiplications by exact zeros
 uint8_t mat_form(const Op& op) {
+  if (op.rot) return QS_FORM_ROT;
   auto zero = [](const cplx& v) { return v.real() == 0.0 && v.imag() == 0.0; };
   if (zero(op.mat[1]) && zero(op.mat[2])) return QS_FORM_DIAG;
   if (zero(op.mat[0]) && zero(op.mat[3])) return QS_FORM_ANTIDIAG;
   return QS_FORM_GENERAL;
+}
+
+// 8-double coefficient slot of one member of a 1Q step
+void write_1q_slot(double* dst, const Op& op) {
+  if (op.rot) {
+    dst[0] = op.c; dst[1] = op.s;
+    dst[2] = op.r0.real(); dst[3] = op.r0.imag();
+    dst[4] = op.r1.real(); dst[5] = op.r1.imag();
+    dst[6] = dst[7] = 0.0;
+  } else {
+    for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+  }
 }
 
 struct Walker {
@@ -388,7 +435,8 @@ struct Walker {
               }
           }
           if (join < 0) {
-            const int need = (op.k == 1) ? 8 * opt.max_group : 2 * (1 << op.k) * (1 << op.k);
+            const int need = (op.k == 1) ? 8 * opt.max_group + 2 * (1 << opt.max_group)
+                                         : 2 * (1 << op.k) * (1 << op.k);
             int nlo = 0;
             for (int b : op.bits) nlo += pending_lo_count(b);
             if (nsteps >= QS_MAX_STEPS || ncoef + need > QS_MAX_COEF || nlo > kMaxLo ||
@@ -403,8 +451,7 @@ struct Walker {
           if (st) {
             st->gpos[f] = (uint8_t)lpos[c];
             st->form[f] = mat_form(op);
-            double* dst = pass->coef + st->coef_off + 8 * f;
-            for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+            write_1q_slot(pass->coef + st->coef_off + 8 * f, op);
             st->r++;
           }
           attach(c, join, f, st);
@@ -422,11 +469,13 @@ struct Walker {
             for (int f = 0; f < op.k; ++f) st->gpos[f] = (uint8_t)lpos[op.bits[f]];
             if (op.k == 1) st->form[0] = mat_form(op);
             double* dst = pass->coef + ncoef;
-            for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+            if (op.k == 1) write_1q_slot(dst, op);
+            else
+              for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
           }
           for (int f = 0; f < op.k; ++f) attach(op.bits[f], nsteps, f, st);
           if (op.k == 1) {
-            ncoef += 8 * opt.max_group;       // room for later members of the group
+            ncoef += 8 * opt.max_group + 2 * (1 << opt.max_group);   // later members + phase table
             step_r[nsteps] = 1;
           } else {
             ncoef += 2 * dim * dim;
@@ -448,6 +497,27 @@ struct Walker {
     }
 
     if (pass) {
+      // phase tables of the steps that hold rotation-form members
+      for (int sidx = 0; sidx < nsteps; ++sidx) {
+        QsStep& st = pass->steps[sidx];
+        if (st.kind != QS_STEP_1Q) continue;
+        bool any = false;
+        for (int f = 0; f < st.r; ++f) any |= st.form[f] == QS_FORM_ROT;
+        if (!any) continue;
+        st.has_phase = 1;
+        st.ph_off = (uint16_t)(st.coef_off + 8 * opt.max_group);
+        for (int m = 0; m < (1 << st.r); ++m) {
+          cplx ph(1.0, 0.0);
+          for (int f = 0; f < st.r; ++f) {
+            if (st.form[f] != QS_FORM_ROT) continue;
+            const double* slot = pass->coef + st.coef_off + 8 * f;
+            const int bit = (m >> (st.r - 1 - f)) & 1;
+            ph *= cplx(slot[2 + 2 * bit], slot[3 + 2 * bit]);
+          }
+          pass->coef[st.ph_off + 2 * m] = ph.real();
+          pass->coef[st.ph_off + 2 * m + 1] = ph.imag();
+        }
+      }
       // flatten the per-step (local, outer) pair lists
       for (int sidx = 0; sidx < nsteps; ++sidx) {
         QsStep& st = pass->steps[sidx];

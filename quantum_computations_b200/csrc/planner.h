@@ -23,6 +23,10 @@ struct Op {
   std::vector<int> bits;
   bool diag = false;
   std::vector<cplx> mat;     // 2^k x 2^k row-major (empty for OP_SIGN)
+  // k == 1 unitaries emitted by the merge pass as  [[c,-s],[s,c]] . diag(r0, r1)
+  bool rot = false;
+  double c = 1.0, s = 0.0;
+  cplx r0 = cplx(1.0, 0.0), r1 = cplx(1.0, 0.0);
   uint64_t mask() const {
     uint64_t m = 0;
     for (int b : bits) m |= 1ull << b;

@@ -82,9 +82,9 @@ QS_HD uint32_t qs_fin_neigh(const QsPass& P, uint32_t x) {
 }
 
 // ---- per-launch tables (tile independent) -----------------------------------------------
-// Entry e (0..63) of a step's table: 0..15 -> jA, 16..31 -> jB, 32..47 -> hi,
-// 48..63 -> sdep.
-#define QS_TAB_ENTRIES 64
+// Entry e (0..79) of a step's table: 0..15 -> jA, 16..47 -> jB, 48..63 -> hi,
+// 64..79 -> sdep.
+#define QS_TAB_ENTRIES 80
 QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint32_t nthr_log2) {
   const QsStep& st = P.steps[s];
   const int nfree = (int)P.T - st.r;
@@ -92,15 +92,15 @@ QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint
   if (e < 16) {
     const int c = lo_bits < 4 ? lo_bits : 4;
     tab->jA[e] = (uint16_t)qs_scatter8((uint32_t)e, st.fpos, c);
-  } else if (e < 32) {
-    const int c = lo_bits - 4 < 0 ? 0 : (lo_bits - 4 > 4 ? 4 : lo_bits - 4);
-    tab->jB[e - 16] = (uint16_t)qs_scatter8((uint32_t)(e - 16), st.fpos + 4, c);
   } else if (e < 48) {
-    const uint32_t jhi = qs_scatter8((uint32_t)(e - 32), st.fpos + nthr_log2, nfree - lo_bits);
-    tab->hi[e - 32] = jhi | (qs_swz(jhi) << 16);
+    const int c = lo_bits - 4 < 0 ? 0 : (lo_bits - 4 > 5 ? 5 : lo_bits - 4);
+    tab->jB[e - 16] = (uint16_t)qs_scatter8((uint32_t)(e - 16), st.fpos + 4, c);
+  } else if (e < 64) {
+    const uint32_t jhi = qs_scatter8((uint32_t)(e - 48), st.fpos + nthr_log2, nfree - lo_bits);
+    tab->hi[e - 48] = jhi | (qs_swz(jhi) << 16);
   } else {
     // amplitude m: matrix factor f is bit (r-1-f) of m and sits at local position gpos[f]
-    const int m = e - 48;
+    const int m = e - 64;
     uint32_t d = 0;
     for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
     tab->sdep[m] = (uint16_t)qs_swz(d);
@@ -221,6 +221,16 @@ QS_HD void qs_mat2_anti(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) 
   a1.y = m[4] * y0 + m[5] * x0;
 }
 
+// real rotation [[c, -s], [s, c]] on a pair of complex amplitudes
+QS_HD void qs_mat2_rot(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
+  const double c = m[0], s = m[1];
+  const double x0 = a0.x, y0 = a0.y, x1 = a1.x, y1 = a1.y;
+  a0.x = c * x0 - s * x1;
+  a0.y = c * y0 - s * y1;
+  a1.x = s * x0 + c * x1;
+  a1.y = s * y0 + c * y1;
+}
+
 // ---- phase: one step ------------------------------------------------------------
 // R group bits; every work item is the 2^R amplitudes that differ only in them.
 // Amplitude m of a work item has local index j0 ^ dep[m]; matrix factor f is bit
@@ -266,7 +276,7 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
     for (int f = 0; f < R; ++f) ng[f] = 0;
   }
 
-  const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 15u];
+  const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
   const uint32_t slo = qs_swz(jlo);
 
   for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthr) {
@@ -293,6 +303,16 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
       for (int m = 0; m < NA; ++m) qs_flip(a[m], (sg >> m) << 31);
     }
     if (!DENSE || st.kind == QS_STEP_1Q) {
+      if (st.has_phase) {
+        const double* ph = P.coef + st.ph_off;
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+          const double pr = ph[2 * m], pi = ph[2 * m + 1];
+          const double x = a[m].x, y = a[m].y;
+          a[m].x = pr * x - pi * y;
+          a[m].y = pr * y + pi * x;
+        }
+      }
 #pragma unroll
       for (int f = 0; f < R; ++f) {
         const double* mat = P.coef + st.coef_off + 8 * f;
@@ -302,6 +322,10 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 #pragma unroll
           for (int m = 0; m < NA; ++m)
             if (!(m & bit)) qs_mat2(mat, a[m], a[m | bit]);
+        } else if (form == QS_FORM_ROT) {
+#pragma unroll
+          for (int m = 0; m < NA; ++m)
+            if (!(m & bit)) qs_mat2_rot(mat, a[m], a[m | bit]);
         } else if (form == QS_FORM_DIAG) {
 #pragma unroll
           for (int m = 0; m < NA; ++m)

@@ -22,6 +22,8 @@ import numpy as np
 from . import _capi
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libqsim_b200.so")
+if os.environ.get("QSIM_LIB"):          # development: try an experimental build of the same library
+    _LIB_PATH = os.environ["QSIM_LIB"]
 
 # Planner knobs (0 = library default); bench.py sweeps these.
 PLAN_OPTIONS = {"tile_bits": 0, "low_bits": 0, "max_group": 0, "max_dense_ops": 0, "lookahead": 0,
