@@ -55,6 +55,7 @@ typedef struct {
   int64_t n_dense;          /* matrix applications inside the steps                             */
   int64_t n_sign;           /* CZ/Z sign pairs                                                  */
   int64_t n_generic;        /* gates on > 4 qubits executed by the out-of-place generic kernel  */
+  int64_t n_warp_syncs;     /* steps followed by a warp-level instead of a block-level barrier  */
 } qsim_plan_stats_t;
 
 const char* qsim_last_error(void);

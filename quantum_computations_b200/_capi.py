@@ -33,6 +33,7 @@ class PlanStats(C.Structure):
         ("n_dense", C.c_int64),
         ("n_sign", C.c_int64),
         ("n_generic", C.c_int64),
+        ("n_warp_syncs", C.c_int64),
     ]
 
     def as_dict(self) -> dict:

@@ -18,6 +18,43 @@ namespace {
 
 int64_t g_launches = 0;
 
+// The emulator runs threads one after the other, so it cannot see a missing
+// barrier.  What it can check is the planner's promise behind every
+// `block_sync == 0`: in step s and step s+1 each warp touches exactly the same set
+// of shared-memory slots.
+int g_ownership_violations = 0;
+
+void slots_of_step(const QsPass& P, int s, const QsStepTab& tab, std::vector<int>& owner) {
+  const QsStep& st = P.steps[s];
+  const uint32_t nwork = 1u << (P.T - st.r);
+  owner.assign((size_t)1 << P.T, -1);
+  for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
+    const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
+    for (uint32_t i = 0, w = tid; w < nwork; ++i, w += QS_THREADS) {
+      const uint32_t j0 = jlo | (tab.hi[i] & 0xffffu);
+      for (int m = 0; m < (1 << st.r); ++m) {
+        uint32_t d = 0;
+        for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
+        owner[j0 | d] = (int)(tid >> 5);
+      }
+    }
+  }
+}
+
+void check_warp_ownership(const QsPass& P, int s, const QsStepTab& tab_s) {
+  static std::vector<int> prev;
+  static int prev_step = -2;
+  static const QsPass* prev_pass = nullptr;
+  std::vector<int> cur;
+  slots_of_step(P, s, tab_s, cur);
+  if (prev_pass == &P && prev_step == s - 1 && P.steps[s - 1].block_sync == 0)
+    for (size_t j = 0; j < cur.size(); ++j)
+      if (cur[j] != prev[j]) { ++g_ownership_violations; break; }
+  prev.swap(cur);
+  prev_step = s;
+  prev_pass = &P;
+}
+
 void emu_pass(const QsPass& P, qs_c128* state, int n) {
   const uint64_t ntiles = 1ull << (n - (int)P.T);
   const int nsteps = (int)P.nsteps;
@@ -48,12 +85,14 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
       qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io,
                     [](qs_c128* dst, const qs_c128* src) { *dst = *src; });
-    for (int s = 0; s < nsteps; ++s)
+    for (int s = 0; s < nsteps; ++s) {
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
         // same variant selection as launch_pass() in kernels.cu
         if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
         else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
       }
+      if (t == 0) check_warp_ownership(P, s, tab[s]);
+    }
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
       qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io, fin_qlo[tid],
                      zmask[nsteps], zmask[nsteps + 1]);
@@ -77,6 +116,8 @@ int emu_generic(const qs::Op& op, qs_c128* state, qs_c128* scratch, int n) {
 
 int execute_plan(const qsim_plan* p, void* state, int n, void* scratch) {
   if (!p || !state) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: null argument");
+  if (g_ownership_violations)
+    return qs::fail(QSIM_ERR_UNSUPPORTED, "emulator: a warp-synchronised step reads another warp's amplitudes");
   if (n != p->n) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: plan was compiled for a different qubit count");
   for (const qs::PlanItem& it : p->items) {
     if (it.generic) {
@@ -85,6 +126,8 @@ int execute_plan(const qsim_plan* p, void* state, int n, void* scratch) {
     } else {
       if ((int)it.pass.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
       emu_pass(it.pass, (qs_c128*)state, n);
+      if (g_ownership_violations)
+        return qs::fail(QSIM_ERR_UNSUPPORTED, "emulator: a warp-synchronised step reads another warp's amplitudes");
     }
   }
   return QSIM_OK;

@@ -156,8 +156,10 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     }
     __syncthreads();
     for (int s = 0; s < nsteps; ++s) {
-      qs_phase_step_any<MAXR, DENSE>(P, s, cur, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s]);
-      __syncthreads();
+      qs_phase_step_any<MAXR, DENSE>(P, s, cur, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s], debug_skip);
+      // inside a run the next step touches only amplitudes of the same warp (plan.h)
+      if (P.steps[s].block_sync) __syncthreads();
+      else __syncwarp();
     }
     if (!(debug_skip & 2))
       qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
@@ -220,7 +222,8 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
     stagger = stagger_env > 0 ? stagger_env : (int)(cycles / occ);
   }
   // QSIM_DEBUG_SKIP (development only): bit 0 skips the global loads, bit 1 the global
-  // stores of a pass, to time the shared-memory/FP64 part on its own (results are garbage)
+  // stores of a pass, bit 2 the matrix arithmetic, to time the parts on their own
+  // (results are garbage)
   static const int debug_skip = [] {
     const char* e = getenv("QSIM_DEBUG_SKIP");
     return e ? atoi(e) : 0;

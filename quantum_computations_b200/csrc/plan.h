@@ -69,7 +69,8 @@ struct QsStep {
   uint8_t  has_sign;             // 1 if the step's sign block is not empty
   uint8_t  form[QS_MAX_R];       // QS_STEP_1Q: shape of each 2x2 (QsMatForm), saves flops
   uint8_t  has_phase;            // 1 if a phase table (2^r complex, indexed by m) precedes the matrices
-  uint8_t  pad0;
+  uint8_t  block_sync;           // 1: __syncthreads() after this step; 0: the next step only needs data
+                                 //    of the same warp (same warp-owned index bits), __syncwarp() is enough
   uint16_t ph_off;               // its offset (in doubles) in QsPass::coef
   uint16_t coef_off;             // first coefficient (in doubles) in QsPass::coef
   // sign block (only pairs touching a group bit)

@@ -568,26 +568,63 @@ struct Walker {
 };
 
 // Order the free local positions of a step: the three fastest thread bits go to
-// positions that differ mod 3 (conflict-free with the XOR-fold swizzle), the
-// rest ascending.
-void order_free_positions(QsStep& st, int T) {
+// positions that differ mod 3 (conflict-free with the XOR-fold swizzle), lanes 3-4
+// next, then the `nwarp` warp-owned positions (thread-id bits 5..7), then the
+// per-thread iteration bits.
+void order_free_positions(QsStep& st, int T, const int* warp_pos, int nwarp) {
   bool used[QS_MAX_T + 1] = {false};
   for (int f = 0; f < st.r; ++f) used[st.gpos[f]] = true;
+  for (int w = 0; w < nwarp; ++w) used[warp_pos[w]] = true;
   std::vector<int> freep;
   for (int p = 0; p < T; ++p)
     if (!used[p]) freep.push_back(p);
-  std::vector<int> first3;
+  std::vector<int> order;
   bool have[3] = {false, false, false};
   for (int p : freep)
-    if (!have[p % 3]) { have[p % 3] = true; first3.push_back(p); }
-  std::vector<int> order = first3;
-  // pad the leading triple from the remaining positions if a residue is missing
+    if (!have[p % 3]) { have[p % 3] = true; order.push_back(p); }
   for (int p : freep)
     if (std::find(order.begin(), order.end(), p) == order.end()) order.push_back(p);
-  if (first3.size() < 3) {
-    // keep deterministic: leading entries are first3 then ascending rest (already so)
-  }
+  if (nwarp > 0) order.insert(order.begin() + 5, warp_pos, warp_pos + nwarp);   // needs >= 5 lane positions
   for (size_t i = 0; i < order.size() && i < QS_MAX_T; ++i) st.fpos[i] = (uint8_t)order[i];
+}
+
+// Split the steps of a pass into runs inside which every warp keeps working on
+// the same 2^(T-3) amplitudes: three tile positions that no step of the run uses
+// as a group bit are tied to the warp number, so steps of a run are separated by
+// __syncwarp() only and the eight warps of a CTA drift apart -- shared-memory
+// traffic of one warp then overlaps the FP64 work of another.
+void assign_runs(QsPass& P) {
+  const int T = (int)P.T;
+  const int nsteps = (int)P.nsteps;
+  int s = 0;
+  while (s < nsteps) {
+    uint32_t used = 0;
+    int e = s, maxr = 0;
+    while (e < nsteps) {
+      uint32_t u = used;
+      const QsStep& st = P.steps[e];
+      for (int f = 0; f < st.r; ++f) u |= 1u << st.gpos[f];
+      const int r = std::max(maxr, (int)st.r);
+      if (T - __builtin_popcount(u) < 3 || T - r < QS_THREADS_LOG2) break;
+      used = u;
+      maxr = r;
+      ++e;
+    }
+    if (e == s) {                       // no room for warp-owned positions: plain block-synchronised step
+      order_free_positions(P.steps[s], T, nullptr, 0);
+      P.steps[s].block_sync = 1;
+      ++s;
+      continue;
+    }
+    int wp[3], nw = 0;
+    for (int p = T - 1; p >= 0 && nw < 3; --p)
+      if (!(used >> p & 1)) wp[nw++] = p;
+    for (int i = s; i < e; ++i) {
+      order_free_positions(P.steps[i], T, wp, 3);
+      P.steps[i].block_sync = (i == e - 1) ? 1 : 0;
+    }
+    s = e;
+  }
 }
 
 }  // namespace
@@ -672,10 +709,11 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
     if (taken.empty())
       return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
     for (size_t idx : taken) done[idx] = 1;
+    assign_runs(P);
     for (uint32_t s = 0; s < P.nsteps; ++s) {
       QsStep& st = P.steps[s];
-      order_free_positions(st, (int)P.T);
       stats.n_steps++;
+      stats.n_warp_syncs += st.block_sync ? 0 : 1;
       stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
     }
     for (size_t idx : taken) stats.n_sign += ops[idx].kind == OP_SIGN ? 1 : 0;

@@ -238,7 +238,7 @@ QS_HD void qs_mat2_rot(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
 // parity(m & W) + qg(m) with W_f = z_f + parity(j0 & ng[f])   (plan.h).
 template <int R, bool DENSE>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                         uint32_t zmask, const QsStepTab& tab) {
+                         uint32_t zmask, const QsStepTab& tab, int debug_skip = 0) {
   const QsStep& st = P.steps[s];
   const uint32_t nwork = 1u << (P.T - R);
   const uint32_t nthr = 1u << nthr_log2;
@@ -302,7 +302,10 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 #pragma unroll
       for (int m = 0; m < NA; ++m) qs_flip(a[m], (sg >> m) << 31);
     }
-    if (!DENSE || st.kind == QS_STEP_1Q) {
+    if (debug_skip & 4) {            // development: shared-memory round trip without the math
+#pragma unroll
+      for (int m = 0; m < NA; ++m) tile[s0 ^ sdep[m]] = a[m];
+    } else if (!DENSE || st.kind == QS_STEP_1Q) {
       if (st.has_phase) {
         const double* ph = P.coef + st.ph_off;
 #pragma unroll
@@ -362,10 +365,11 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 // of the calling kernel); DENSE says whether dense (k >= 2) steps may occur.
 template <int MAXR, bool DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                             uint32_t zmask, const QsStepTab& tab) {
+                             uint32_t zmask, const QsStepTab& tab, int debug_skip = 0) {
   const int r = P.steps[s].r;
-  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, tab);
-  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
-  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
-  else if (MAXR >= 4 && r == 4) qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zmask, tab);
+  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
+  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
+  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
+  else if (MAXR >= 4 && r == 4)
+    qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
 }
