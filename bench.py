@@ -42,6 +42,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "gates/sec (30q c128 random circuit, depth 200)"
+# dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_full_k_tile_pass_n30.csv (17.18 GB + 17.12 GB)
+NCU_TRAFFIC_N30 = 34.30e9
 
 
 def parse_args():
@@ -245,8 +248,11 @@ def run_b200(args):
     bytes_per_launch = 2.0 * 16.0 * (2.0 ** n)
     launch_ms = kernel_ms / max(1, args.steps * passes)
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    traffic = args.traffic_bytes
+    if traffic is None and n == 30 and not any(opts.values()):
+        traffic = NCU_TRAFFIC_N30
     roofline = {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": args.traffic_bytes, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launches_per_step": passes,
                 "mean_launch_ms": launch_ms}
 
