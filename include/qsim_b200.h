@@ -136,11 +136,13 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* 
  * rank number.  Exchanging global qubit qg with local qubit ql moves, on every rank,
  * the half of the shard whose ql-bit differs from the rank's qg-bit.  These two
  * kernels gather that half into a contiguous send buffer and scatter the received
- * half back; the transfer itself is the caller's (NCCL send/recv or P2P copy). */
+ * half back; the transfer itself is the caller's (NCCL send/recv or P2P copy).
+ * first/count select a chunk of the 2^(n_local-1) travelling amplitudes (for pipelining);
+ * the buffer holds `count` amplitudes. */
 int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit,
-                   void* stream);
+                   uint64_t first, uint64_t count, void* stream);
 int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit,
-                     void* stream);
+                     uint64_t first, uint64_t count, void* stream);
 
 /* Launch statistics since process start (kernels launched by this library). */
 int64_t qsim_launch_count(void);

@@ -335,26 +335,30 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* 
   return QSIM_OK;
 }
 
-int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, void*) {
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
+                   uint64_t count, void*) {
   if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
   if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
     return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
   const int pos = n_local - 1 - local_qubit;
   const qs_c128* s = (const qs_c128*)shard;
   qs_c128* b = (qs_c128*)sendbuf;
-  for (uint64_t r = 0; r < (1ull << (n_local - 1)); ++r) b[r] = s[qs_insert_bit(r, pos, (uint64_t)(1 - keep_bit))];
+  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: chunk out of range");
+  for (uint64_t r = 0; r < count; ++r) b[r] = s[qs_insert_bit(first + r, pos, (uint64_t)(1 - keep_bit))];
   ++g_launches;
   return QSIM_OK;
 }
 
-int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, void*) {
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
+                     uint64_t count, void*) {
   if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
   if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
     return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
   const int pos = n_local - 1 - local_qubit;
   qs_c128* s = (qs_c128*)shard;
   const qs_c128* b = (const qs_c128*)recvbuf;
-  for (uint64_t r = 0; r < (1ull << (n_local - 1)); ++r) s[qs_insert_bit(r, pos, (uint64_t)(1 - keep_bit))] = b[r];
+  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: chunk out of range");
+  for (uint64_t r = 0; r < count; ++r) s[qs_insert_bit(first + r, pos, (uint64_t)(1 - keep_bit))] = b[r];
   ++g_launches;
   return QSIM_OK;
 }

@@ -273,17 +273,17 @@ __global__ void k_generic(const qs_c128* __restrict__ in, qs_c128* __restrict__ 
 }
 
 __global__ void k_swap_pack(const qs_c128* __restrict__ shard, qs_c128* __restrict__ buf, int pos,
-                            uint64_t bit, uint64_t count) {
+                            uint64_t bit, uint64_t first, uint64_t count) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
        r += (uint64_t)gridDim.x * blockDim.x)
-    buf[r] = shard[qs_insert_bit(r, pos, bit)];
+    buf[r] = shard[qs_insert_bit(first + r, pos, bit)];
 }
 
 __global__ void k_swap_unpack(qs_c128* __restrict__ shard, const qs_c128* __restrict__ buf, int pos,
-                              uint64_t bit, uint64_t count) {
+                              uint64_t bit, uint64_t first, uint64_t count) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
        r += (uint64_t)gridDim.x * blockDim.x)
-    shard[qs_insert_bit(r, pos, bit)] = buf[r];
+    shard[qs_insert_bit(first + r, pos, bit)] = buf[r];
 }
 
 unsigned stream_grid(const DevCtx* ctx, uint64_t count, int threads) {
@@ -666,31 +666,35 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* 
   return QSIM_OK;
 }
 
-int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, void* stream) {
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
+                   uint64_t count, void* stream) {
   if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
   if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
     return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
   DevCtx* ctx = nullptr;
   int rc = bind_device(shard, &ctx);
   if (rc != QSIM_OK) return rc;
-  const uint64_t count = 1ull << (n_local - 1);
+  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: chunk out of range");
+  if (count == 0) return QSIM_OK;
   k_swap_pack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const qs_c128*)shard, (qs_c128*)sendbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), count);
+      (const qs_c128*)shard, (qs_c128*)sendbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), first, count);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;
 }
 
-int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, void* stream) {
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
+                     uint64_t count, void* stream) {
   if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
   if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
     return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
   DevCtx* ctx = nullptr;
   int rc = bind_device(shard, &ctx);
   if (rc != QSIM_OK) return rc;
-  const uint64_t count = 1ull << (n_local - 1);
+  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: chunk out of range");
+  if (count == 0) return QSIM_OK;
   k_swap_unpack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
-      (qs_c128*)shard, (const qs_c128*)recvbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), count);
+      (qs_c128*)shard, (const qs_c128*)recvbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), first, count);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

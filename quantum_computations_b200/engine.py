@@ -57,6 +57,10 @@ class CudaBackend:
         _capi.declare(self.lib)
         if self.lib.qsim_has_cuda() != 1:
             raise RuntimeError("libqsim_b200.so was built without CUDA kernels")
+        self._side_streams = []
+
+    def pipeline(self, nstages: int) -> "_StreamPipeline":
+        return _StreamPipeline(self, nstages)
 
     # -- memory ------------------------------------------------------------------
     def empty(self, count: int):
@@ -97,6 +101,42 @@ class CudaBackend:
         """Pinned host buffer viewed as a complex128 ndarray (for `out=`)."""
         t = self.torch.empty(int(count), dtype=self.torch.complex128, pin_memory=True)
         return t.numpy()
+
+
+class _StreamPipeline:
+    """A few side streams with event dependencies between them (used by the sharded
+    swap to overlap gather, exchange and scatter)."""
+
+    def __init__(self, backend: "CudaBackend", nstages: int):
+        torch = backend.torch
+        self.torch = torch
+        self.device = backend.device
+        if len(backend._side_streams) < nstages:
+            backend._side_streams += [torch.cuda.Stream(self.device)
+                                      for _ in range(nstages - len(backend._side_streams))]
+        self.streams = backend._side_streams[:nstages]
+        self.main = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(self.main)
+        for st in self.streams:
+            st.wait_event(start)
+
+    def stage(self, i: int):
+        return self.torch.cuda.stream(self.streams[i])
+
+    def record(self):
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
+    def wait(self, ev) -> None:
+        self.torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def join(self) -> None:
+        for st in self.streams:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            self.main.wait_event(ev)
 
 
 _backend_lock = threading.Lock()

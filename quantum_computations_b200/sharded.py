@@ -89,6 +89,7 @@ class ShardedState:
         self.buf = self.backend.empty(1 << self.n_local)
         self.swaps = 0
         self.swap_seconds = 0.0
+        self._swap_bufs = None
         # how to view a backend buffer as a torch tensor for the communicator
         self._as_torch = as_torch or (lambda b: b)
 
@@ -119,31 +120,51 @@ class ShardedState:
         return float(np.sqrt(self.comm.allreduce_sum(out[:1])[0]))
 
     # -- swaps -----------------------------------------------------------------------------------
+    CHUNK_LOG2 = 26            # amplitudes per pipeline chunk (1 GiB)
+
     def swap(self, global_phys: int, local_phys: int) -> None:
-        """Exchange physical rank bit ``global_phys`` with physical local bit ``local_phys``."""
+        """Exchange physical rank bit ``global_phys`` with physical local bit ``local_phys``.
+
+        The travelling half shard is cut into chunks that flow through a three-stage
+        pipeline on three streams -- gather (``qsim_swap_pack``), NVLink exchange with
+        the partner rank, scatter (``qsim_swap_unpack``) -- with two send and two
+        receive buffers, so the HBM-side gather/scatter hides behind the transfer."""
         import time
         be, lib = self.backend, self.backend.lib
         gi = global_phys - self.n_local            # bit of the rank number
         keep = (self.comm.rank >> gi) & 1
         partner = self.comm.rank ^ (1 << gi)
         half = 1 << (self.n_local - 1)
+        qubit = self.n_local - 1 - local_phys      # local reference-style qubit number
+        chunk = min(half, 1 << self.CHUNK_LOG2)
+        nchunks = half // chunk
         be.synchronize()                           # so the timer below sees the swap alone
         t0 = time.perf_counter()
-        if local_phys == self.n_local - 1:
-            # halves are contiguous: send the half with top bit != keep, receive into it
-            lo = (1 - keep) * half
-            view = self._as_torch(self.buf)[lo:lo + half]
-            recv = self._as_torch(be.empty(half))
-            self.comm.exchange(view, recv, partner)
-            view.copy_(recv)
-        else:
-            send, recv = be.empty(half), be.empty(half)
-            qubit = self.n_local - 1 - local_phys  # local reference-style qubit number
-            _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), be.ptr(send), self.n_local, qubit, keep,
-                                                be.stream()))
-            self.comm.exchange(self._as_torch(send), self._as_torch(recv), partner)
-            _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), be.ptr(recv), self.n_local, qubit, keep,
-                                                  be.stream()))
+        if self._swap_bufs is None or self._swap_bufs[0].shape[0] != chunk:
+            self._swap_bufs = [be.empty(chunk) for _ in range(4)]
+        send, recv = self._swap_bufs[:2], self._swap_bufs[2:]
+        pipe = be.pipeline(3)                      # stream contexts + events (no-ops on the host emulator)
+        packed, received, unpacked = {}, {}, {}
+        for c in range(nchunks):
+            first = c * chunk
+            with pipe.stage(0):                    # gather chunk c (its send buffer was last used by chunk c-2)
+                if c >= 2:
+                    pipe.wait(received[c - 2])
+                _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), be.ptr(send[c % 2]), self.n_local, qubit,
+                                                    keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
+                packed[c] = pipe.record()
+            with pipe.stage(1):                    # exchange (its receive buffer was last used by chunk c-2)
+                pipe.wait(packed[c])
+                if c >= 2:
+                    pipe.wait(unpacked[c - 2])
+                self.comm.exchange(self._as_torch(send[c % 2]), self._as_torch(recv[c % 2]), partner)
+                received[c] = pipe.record()
+            with pipe.stage(2):                    # scatter chunk c into the places chunk c left
+                pipe.wait(received[c])
+                _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), be.ptr(recv[c % 2]), self.n_local, qubit,
+                                                      keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
+                unpacked[c] = pipe.record()
+        pipe.join()
         be.synchronize()
         self.swap_seconds += time.perf_counter() - t0
         self.swaps += 1
@@ -227,40 +248,72 @@ class ShardedSimulator:
             cursor[bit] = c
             return lst[c] if c < len(lst) else 1 << 60
 
-        schedule, segment = [], []
+        schedule = []
 
-        def flush():
+        def flush(segment):
             if not segment:
                 return
-            plan = engine.Plan(st.backend, nloc, list(segment), self.plan_options)
+            plan = engine.Plan(st.backend, nloc, segment, self.plan_options)
             schedule.append(("plan", plan))
             self.stats["segments"] += 1
             self.stats["passes"] += plan.stats["n_passes"]
             self.stats["local_gates"] += len(segment)
-            segment.clear()
 
         saved = st.phys
         try:
-            for idx, (bits, m, is_diag) in enumerate(ops):
-                st.phys = phys                         # _restrict_diagonal reads the layout
-                p_bits = [phys[b] for b in bits]
-                if is_diag:
-                    if any(p >= nloc for p in p_bits):
-                        p_bits, m = self._restrict_diagonal(p_bits, m)
-                    segment.append(([nloc - 1 - p for p in p_bits], m))
-                    continue
+            st.phys = phys                             # _restrict_diagonal reads the layout
+            pending = list(range(len(ops)))
+            while pending:
+                # Classify what could run in the current layout.  A gate that cannot
+                # (non-diagonal on a rank bit) blocks its qubits; gates behind it are held
+                # back only if they do not commute with what is blocked (diagonal gates
+                # commute with each other).
+                ready, deferred = [], []
+                blocked_full, blocked_diag = set(), set()
+                for idx in pending:
+                    bits, m, is_diag = ops[idx]
+                    free = not (blocked_full & set(bits)) and (is_diag or not (blocked_diag & set(bits)))
+                    if free and (is_diag or all(phys[b] < nloc for b in bits)):
+                        ready.append(idx)
+                    else:
+                        deferred.append(idx)
+                        (blocked_diag if is_diag else blocked_full).update(bits)
+
+                def run_ready():
+                    segment = []
+                    for idx in ready:
+                        bits, m, is_diag = ops[idx]
+                        p_bits = [phys[b] for b in bits]
+                        if is_diag and any(p >= nloc for p in p_bits):
+                            p_bits, m = self._restrict_diagonal(p_bits, m)
+                        segment.append(([nloc - 1 - p for p in p_bits], m))
+                    flush(segment)
+                    ready.clear()
+
+                if not deferred:
+                    run_ready()
+                    break
+                # Bring in the rank bits of the first blocked gate.  Ready gates are NOT run
+                # at every swap: gates that touch neither swapped qubit commute with the swap,
+                # so they keep accumulating into bigger, better-packed fused plans.  They must
+                # run first only if the evicted qubit still has a non-diagonal gate among them.
+                head = deferred[0]
+                bits = ops[head][0]
                 for b in bits:
                     if phys[b] < nloc:
                         continue
-                    # bring logical bit b into the shard: evict the local bit needed latest
-                    flush()
+                    busy = set()
+                    for idx in ready:
+                        if not ops[idx][2]:
+                            busy.update(ops[idx][0])
                     local_logical = [l for l in range(st.n) if phys[l] < nloc and l not in bits]
-                    victim = max(local_logical, key=lambda l: (next_use(l, idx), phys[l]))
+                    victim = max(local_logical, key=lambda l: (l not in busy, next_use(l, head), phys[l]))
+                    if victim in busy:
+                        run_ready()
                     schedule.append(("swap", phys[b], phys[victim]))
                     phys[b], phys[victim] = phys[victim], phys[b]
                     self.stats["swaps"] += 1
-                segment.append(([nloc - 1 - phys[b] for b in bits], m))
-            flush()
+                pending = sorted(ready + deferred)
         finally:
             st.phys = saved
         self._schedule = schedule

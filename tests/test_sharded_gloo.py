@@ -46,6 +46,7 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
         vecs = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (n - 2)
         st = sharded.ShardedState(n, comm, backend=be, as_torch=torch.from_numpy)
         st.set_product(vecs)
+        sharded.ShardedState.CHUNK_LOG2 = 5                 # several pipeline chunks per swap even at this size
         sim = sharded.ShardedSimulator(circ, st, plan_options=dict(tile_bits=6, low_bits=2))
         sim.run()
         nrm = st.norm()
