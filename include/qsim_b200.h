@@ -144,6 +144,19 @@ int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubi
 int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit,
                      uint64_t first, uint64_t count, void* stream);
 
+/* ---- peer-to-peer staging for the swaps (one process per GPU) -----------------------
+ * The travelling half shard moves with the copy engines, not with SM kernels: every
+ * rank packs a chunk into a library-allocated staging buffer, exports it once through
+ * CUDA IPC, and the partner PULLS it over NVLink with cudaMemcpyAsync while both GPUs'
+ * SMs keep gathering / scattering the neighbouring chunks.  Ordering between the two
+ * processes is the caller's (a stream-ordered token exchange, see sharded.py). */
+int qsim_peer_alloc(int device, uint64_t bytes, void** out_ptr);       /* cudaMalloc                      */
+int qsim_peer_free(void* ptr);
+int qsim_ipc_export(void* ptr, unsigned char* handle64);               /* 64-byte cudaIpcMemHandle_t      */
+int qsim_ipc_import(int device, const unsigned char* handle64, void** out_ptr);
+int qsim_ipc_release(void* imported_ptr);
+int qsim_peer_copy(void* dst, const void* src, uint64_t bytes, void* stream);
+
 /* Launch statistics since process start (kernels launched by this library). */
 int64_t qsim_launch_count(void);
 

@@ -8,6 +8,7 @@
 // the plan logic and the index arithmetic without a GPU.  The product package
 // never loads it: quantum_computations_b200.engine binds libqsim_b200.so only
 // and raises when that library or a CUDA device is missing.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -152,6 +153,22 @@ extern "C" {
 
 int qsim_has_cuda(void) { return 0; }
 int64_t qsim_launch_count(void) { return g_launches; }
+
+// peer staging: the emulator has one address space; these are plain host operations
+int qsim_peer_alloc(int, uint64_t bytes, void** out_ptr) {
+  if (!out_ptr || bytes == 0) return qs::fail(QSIM_ERR_ARG, "qsim_peer_alloc: bad argument");
+  *out_ptr = malloc(bytes);
+  return *out_ptr ? QSIM_OK : qs::fail(QSIM_ERR_NOMEM, "out of host memory");
+}
+int qsim_peer_free(void* ptr) { free(ptr); return QSIM_OK; }
+int qsim_ipc_export(void*, unsigned char*) { return qs::fail(QSIM_ERR_UNSUPPORTED, "no IPC in the host emulator"); }
+int qsim_ipc_import(int, const unsigned char*, void**) { return qs::fail(QSIM_ERR_UNSUPPORTED, "no IPC in the host emulator"); }
+int qsim_ipc_release(void*) { return QSIM_OK; }
+int qsim_peer_copy(void* dst, const void* src, uint64_t bytes, void*) {
+  if (!dst || !src) return qs::fail(QSIM_ERR_ARG, "qsim_peer_copy: null argument");
+  memcpy(dst, src, bytes);
+  return QSIM_OK;
+}
 
 int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void*) {
   return execute_plan(p, state, n_qubits, scratch);

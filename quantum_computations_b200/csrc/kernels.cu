@@ -486,6 +486,47 @@ int qsim_has_cuda(void) { return 1; }
 
 int64_t qsim_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int qsim_peer_alloc(int device, uint64_t bytes, void** out_ptr) {
+  if (!out_ptr || bytes == 0) return qs::fail(QSIM_ERR_ARG, "qsim_peer_alloc: bad argument");
+  QS_CUDA(cudaSetDevice(device));
+  QS_CUDA(cudaMalloc(out_ptr, bytes));
+  return QSIM_OK;
+}
+
+int qsim_peer_free(void* ptr) {
+  if (ptr) QS_CUDA(cudaFree(ptr));
+  return QSIM_OK;
+}
+
+int qsim_ipc_export(void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle64) return qs::fail(QSIM_ERR_ARG, "qsim_ipc_export: null argument");
+  cudaIpcMemHandle_t h;
+  QS_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return QSIM_OK;
+}
+
+int qsim_ipc_import(int device, const unsigned char* handle64, void** out_ptr) {
+  if (!handle64 || !out_ptr) return qs::fail(QSIM_ERR_ARG, "qsim_ipc_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  QS_CUDA(cudaSetDevice(device));
+  QS_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return QSIM_OK;
+}
+
+int qsim_ipc_release(void* imported_ptr) {
+  if (imported_ptr) QS_CUDA(cudaIpcCloseMemHandle(imported_ptr));
+  return QSIM_OK;
+}
+
+int qsim_peer_copy(void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!dst || !src) return qs::fail(QSIM_ERR_ARG, "qsim_peer_copy: null argument");
+  QS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return QSIM_OK;
+}
+
 int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void* stream) {
   return execute_plan(p, state, n_qubits, scratch, stream);
 }

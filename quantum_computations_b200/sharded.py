@@ -89,7 +89,7 @@ class ShardedState:
         self.buf = self.backend.empty(1 << self.n_local)
         self.swaps = 0
         self.swap_seconds = 0.0
-        self._swap_bufs = None
+        self._peer = None
         # how to view a backend buffer as a torch tensor for the communicator
         self._as_torch = as_torch or (lambda b: b)
 
@@ -122,13 +122,59 @@ class ShardedState:
     # -- swaps -----------------------------------------------------------------------------------
     CHUNK_LOG2 = 26            # amplitudes per pipeline chunk (1 GiB)
 
+    def _peer_setup(self, chunk: int):
+        """Allocate the four staging chunks with the library (plain cudaMalloc, so they can be
+        exported through CUDA IPC) and open every other rank's send chunks once."""
+        import os
+        be, lib = self.backend, self.backend.lib
+        if self._peer is not None and self._peer["chunk"] == chunk:
+            return self._peer
+        use_ipc = getattr(be, "name", "") == "cuda" and os.environ.get("QSIM_SWAP_IPC", "1") != "0"
+        peer = {"chunk": chunk, "ipc": use_ipc}
+        if not use_ipc:
+            peer["send"] = [be.empty(chunk) for _ in range(2)]
+            peer["recv"] = [be.empty(chunk) for _ in range(2)]
+            self._peer = peer
+            return peer
+        import torch
+        dev = be.device.index
+        ptrs = []
+        for _ in range(4):
+            out = C.c_void_p()
+            _capi.check(lib, lib.qsim_peer_alloc(dev, C.c_uint64(16 * chunk), C.byref(out)))
+            ptrs.append(out.value)
+        peer["send_ptr"], peer["recv_ptr"] = ptrs[:2], ptrs[2:]
+        handles = []
+        for p in peer["send_ptr"]:
+            h = C.create_string_buffer(64)
+            _capi.check(lib, lib.qsim_ipc_export(C.c_void_p(p), h))
+            handles.append(h.raw)
+        gathered = [None] * self.comm.size
+        self.comm.dist.all_gather_object(gathered, handles, group=self.comm.group)
+        peer["remote_send"] = {}
+        for r, hs in enumerate(gathered):
+            if r == self.comm.rank:
+                continue
+            opened = []
+            for h in hs:
+                out = C.c_void_p()
+                _capi.check(lib, lib.qsim_ipc_import(dev, h, C.byref(out)))
+                opened.append(out.value)
+            peer["remote_send"][r] = opened
+        peer["token_out"] = torch.zeros(2, dtype=torch.float64, device=be.device)
+        peer["token_in"] = torch.zeros(2, dtype=torch.float64, device=be.device)
+        self._peer = peer
+        return peer
+
     def swap(self, global_phys: int, local_phys: int) -> None:
         """Exchange physical rank bit ``global_phys`` with physical local bit ``local_phys``.
 
         The travelling half shard is cut into chunks that flow through a three-stage
-        pipeline on three streams -- gather (``qsim_swap_pack``), NVLink exchange with
-        the partner rank, scatter (``qsim_swap_unpack``) -- with two send and two
-        receive buffers, so the HBM-side gather/scatter hides behind the transfer."""
+        pipeline on three streams: gather (``qsim_swap_pack``) into a staging chunk,
+        transfer, scatter (``qsim_swap_unpack``).  On GPUs the transfer is a copy-engine
+        PULL of the partner's staging chunk over NVLink (CUDA IPC + ``qsim_peer_copy``),
+        ordered between the two processes by a stream-ordered NCCL token exchange, so
+        no SM is spent on communication; elsewhere (gloo tests) it is a send/recv."""
         import time
         be, lib = self.backend, self.backend.lib
         gi = global_phys - self.n_local            # bit of the rank number
@@ -138,32 +184,55 @@ class ShardedState:
         qubit = self.n_local - 1 - local_phys      # local reference-style qubit number
         chunk = min(half, 1 << self.CHUNK_LOG2)
         nchunks = half // chunk
+        peer = self._peer_setup(chunk)
+        ipc = peer["ipc"]
         be.synchronize()                           # so the timer below sees the swap alone
         t0 = time.perf_counter()
-        if self._swap_bufs is None or self._swap_bufs[0].shape[0] != chunk:
-            self._swap_bufs = [be.empty(chunk) for _ in range(4)]
-        send, recv = self._swap_bufs[:2], self._swap_bufs[2:]
+        if ipc:
+            send_ptr, recv_ptr = peer["send_ptr"], peer["recv_ptr"]
+            remote = peer["remote_send"][partner]
+        else:
+            send_ptr = [be.ptr(b) for b in peer["send"]]
+            recv_ptr = [be.ptr(b) for b in peer["recv"]]
         pipe = be.pipeline(3)                      # stream contexts + events (no-ops on the host emulator)
-        packed, received, unpacked = {}, {}, {}
+        packed, ordered, received, unpacked = {}, {}, {}, {}
+
+        def token():                               # both ranks have reached this point of their comm streams
+            self.comm.exchange(peer["token_out"], peer["token_in"], partner)
+
         for c in range(nchunks):
             first = c * chunk
-            with pipe.stage(0):                    # gather chunk c (its send buffer was last used by chunk c-2)
+            with pipe.stage(0):
+                # send[c%2] was last read by the partner's pull of chunk c-2, which precedes the
+                # partner's token c-1 on its comm stream (IPC), resp. by our own send c-2
                 if c >= 2:
-                    pipe.wait(received[c - 2])
-                _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), be.ptr(send[c % 2]), self.n_local, qubit,
-                                                    keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
+                    pipe.wait(ordered[c - 1] if ipc else received[c - 2])
+                _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), C.c_void_p(send_ptr[c % 2]), self.n_local,
+                                                    qubit, keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
                 packed[c] = pipe.record()
-            with pipe.stage(1):                    # exchange (its receive buffer was last used by chunk c-2)
+            with pipe.stage(1):
                 pipe.wait(packed[c])
                 if c >= 2:
-                    pipe.wait(unpacked[c - 2])
-                self.comm.exchange(self._as_torch(send[c % 2]), self._as_torch(recv[c % 2]), partner)
+                    pipe.wait(unpacked[c - 2])     # recv[c%2] is free again
+                if ipc:
+                    token()                        # partner's chunk c is packed too
+                    ordered[c] = pipe.record()
+                    _capi.check(lib, lib.qsim_peer_copy(C.c_void_p(recv_ptr[c % 2]), C.c_void_p(remote[c % 2]),
+                                                        C.c_uint64(16 * chunk), be.stream()))
+                    self.comm.bytes_exchanged += 16 * chunk
+                else:
+                    self.comm.exchange(self._as_torch(peer["send"][c % 2]), self._as_torch(peer["recv"][c % 2]),
+                                       partner)
                 received[c] = pipe.record()
-            with pipe.stage(2):                    # scatter chunk c into the places chunk c left
+            with pipe.stage(2):
                 pipe.wait(received[c])
-                _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), be.ptr(recv[c % 2]), self.n_local, qubit,
-                                                      keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
+                _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), C.c_void_p(recv_ptr[c % 2]), self.n_local,
+                                                      qubit, keep, C.c_uint64(first), C.c_uint64(chunk),
+                                                      be.stream()))
                 unpacked[c] = pipe.record()
+        if ipc:
+            with pipe.stage(1):
+                token()                            # the partner has pulled everything: staging is reusable
         pipe.join()
         be.synchronize()
         self.swap_seconds += time.perf_counter() - t0
