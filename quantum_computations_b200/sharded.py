@@ -124,7 +124,7 @@ class ShardedState:
 
     def _peer_setup(self, chunk: int):
         """Allocate the four staging chunks with the library (plain cudaMalloc, so they can be
-        exported through CUDA IPC) and open every other rank's send chunks once."""
+        exported through CUDA IPC) and open every other rank's receive chunks once."""
         import os
         be, lib = self.backend, self.backend.lib
         if self._peer is not None and self._peer["chunk"] == chunk:
@@ -145,13 +145,13 @@ class ShardedState:
             ptrs.append(out.value)
         peer["send_ptr"], peer["recv_ptr"] = ptrs[:2], ptrs[2:]
         handles = []
-        for p in peer["send_ptr"]:
+        for p in peer["recv_ptr"]:
             h = C.create_string_buffer(64)
             _capi.check(lib, lib.qsim_ipc_export(C.c_void_p(p), h))
             handles.append(h.raw)
         gathered = [None] * self.comm.size
         self.comm.dist.all_gather_object(gathered, handles, group=self.comm.group)
-        peer["remote_send"] = {}
+        peer["remote_recv"] = {}
         for r, hs in enumerate(gathered):
             if r == self.comm.rank:
                 continue
@@ -160,7 +160,7 @@ class ShardedState:
                 out = C.c_void_p()
                 _capi.check(lib, lib.qsim_ipc_import(dev, h, C.byref(out)))
                 opened.append(out.value)
-            peer["remote_send"][r] = opened
+            peer["remote_recv"][r] = opened
         peer["token_out"] = torch.zeros(2, dtype=torch.float64, device=be.device)
         peer["token_in"] = torch.zeros(2, dtype=torch.float64, device=be.device)
         self._peer = peer
@@ -190,49 +190,63 @@ class ShardedState:
         t0 = time.perf_counter()
         if ipc:
             send_ptr, recv_ptr = peer["send_ptr"], peer["recv_ptr"]
-            remote = peer["remote_send"][partner]
+            remote = peer["remote_recv"][partner]
         else:
             send_ptr = [be.ptr(b) for b in peer["send"]]
             recv_ptr = [be.ptr(b) for b in peer["recv"]]
         pipe = be.pipeline(3)                      # stream contexts + events (no-ops on the host emulator)
-        packed, ordered, received, unpacked = {}, {}, {}, {}
+        packed, ordered, moved, unpacked = {}, {}, {}, {}
 
         def token():                               # both ranks have reached this point of their comm streams
             self.comm.exchange(peer["token_out"], peer["token_in"], partner)
 
-        for c in range(nchunks):
-            first = c * chunk
+        def pack(c):
             with pipe.stage(0):
-                # send[c%2] was last read by the partner's pull of chunk c-2, which precedes the
-                # partner's token c-1 on its comm stream (IPC), resp. by our own send c-2
                 if c >= 2:
-                    pipe.wait(ordered[c - 1] if ipc else received[c - 2])
+                    pipe.wait(moved[c - 2])        # send[c%2] has left (our own push / send of chunk c-2)
                 _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), C.c_void_p(send_ptr[c % 2]), self.n_local,
-                                                    qubit, keep, C.c_uint64(first), C.c_uint64(chunk), be.stream()))
+                                                    qubit, keep, C.c_uint64(c * chunk), C.c_uint64(chunk),
+                                                    be.stream()))
                 packed[c] = pipe.record()
+
+        def unpack(c):
+            with pipe.stage(2):
+                # IPC: the partner's push of chunk c precedes its token c+1 on its comm stream
+                pipe.wait(ordered[c + 1] if ipc else moved[c])
+                _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), C.c_void_p(recv_ptr[c % 2]), self.n_local,
+                                                      qubit, keep, C.c_uint64(c * chunk), C.c_uint64(chunk),
+                                                      be.stream()))
+                unpacked[c] = pipe.record()
+
+        for c in range(nchunks):
+            pack(c)
             with pipe.stage(1):
                 pipe.wait(packed[c])
                 if c >= 2:
-                    pipe.wait(unpacked[c - 2])     # recv[c%2] is free again
+                    pipe.wait(unpacked[c - 2])     # our recv[c%2] is free again
                 if ipc:
-                    token()                        # partner's chunk c is packed too
+                    # token c: both chunks c are packed and both recv[c%2] are free -> PUSH ours
+                    # into the partner's staging with the copy engine (writes are the fast
+                    # direction of NVLink P2P)
+                    token()
                     ordered[c] = pipe.record()
-                    _capi.check(lib, lib.qsim_peer_copy(C.c_void_p(recv_ptr[c % 2]), C.c_void_p(remote[c % 2]),
+                    _capi.check(lib, lib.qsim_peer_copy(C.c_void_p(remote[c % 2]), C.c_void_p(send_ptr[c % 2]),
                                                         C.c_uint64(16 * chunk), be.stream()))
                     self.comm.bytes_exchanged += 16 * chunk
                 else:
                     self.comm.exchange(self._as_torch(peer["send"][c % 2]), self._as_torch(peer["recv"][c % 2]),
                                        partner)
-                received[c] = pipe.record()
-            with pipe.stage(2):
-                pipe.wait(received[c])
-                _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), C.c_void_p(recv_ptr[c % 2]), self.n_local,
-                                                      qubit, keep, C.c_uint64(first), C.c_uint64(chunk),
-                                                      be.stream()))
-                unpacked[c] = pipe.record()
+                moved[c] = pipe.record()
+            if ipc:
+                if c >= 1:
+                    unpack(c - 1)
+            else:
+                unpack(c)
         if ipc:
             with pipe.stage(1):
-                token()                            # the partner has pulled everything: staging is reusable
+                token()                            # every push has landed on both sides
+                ordered[nchunks] = pipe.record()
+            unpack(nchunks - 1)
         pipe.join()
         be.synchronize()
         self.swap_seconds += time.perf_counter() - t0
