@@ -1,10 +1,16 @@
 """Multi-GPU arm of bench.py (torchrun, one rank per GPU, NCCL over NVLink).
 
 Configuration C5: the same random-circuit generator on a register sharded by its
-top log2(N) qubits, 31 local qubits per GPU (so N = 8 is the 34-qubit case of
-BASELINE.json; 2 and 4 GPUs run 32 and 33 qubits -- per-GPU work is fixed, weak
-scaling).  Non-diagonal gates on a rank qubit trigger a global<->local swap
-(half a shard out and half a shard in per GPU).
+top log2(N) qubits.  Default: 30 local qubits per GPU, i.e. 31 / 32 / 33 qubits on
+2 / 4 / 8 GPUs -- exactly the per-GPU state of the N = 1 bench, so the runs form a
+weak-scaling series; `--qubits 34` runs the 34-qubit case of BASELINE.json (31
+local qubits on 8 GPUs; recorded in profiles/).  Non-diagonal gates on a rank qubit
+trigger a global<->local swap (half a shard out and half a shard in per GPU).
+
+A gate on an n-qubit register touches 2^n amplitudes, so gates/s alone is not
+comparable across register sizes: `value` is gates/s x 2^(n-30), the rate in units
+of 30-qubit gate applications (identical to plain gates/s at N = 1); the raw figure
+is kept in config.raw_gates_per_s.
 """
 from __future__ import annotations
 
@@ -24,7 +30,7 @@ def run_sharded(args, world, rank, local_rank):
 
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = world.bit_length() - 1
-    n = args.qubits or (31 + g)
+    n = args.qubits or (30 + g)
     backend = engine.get_backend(local_rank)
     comm = sharded.Comm()
     comm.device = torch.device("cuda", local_rank)
@@ -79,15 +85,17 @@ def run_sharded(args, world, rank, local_rank):
         achieved = 2.0 * shard_bytes / (compute_ms * 1e-3) / 1e9
         half_bytes = shard_bytes / 2
         nvlink = half_bytes / (swap_ms * 1e-3) / 1e9 if swaps else None
+        raw = args.steps * ngates / (total_ms * 1e-3)
         line = {
-            "metric": METRIC, "value": args.steps * ngates / (total_ms * 1e-3), "unit": "gates/s", "n_gpus": world,
+            "metric": METRIC, "value": raw * 2.0 ** (n - 30), "unit": "gates/s x 2^(n-30) (30-qubit-equivalent gates/s)",
+            "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
             "config": {"workload": f"C5: {n}-qubit complex128 random circuit, depth {args.depth}, {ngates} gates, "
                                    f"sharded over {world} GPUs by the top {g} qubits ({state.n_local} local qubits, "
                                    f"{shard_bytes / 2 ** 30:.0f} GiB per GPU); shards exceed L2, no flush needed",
                        "plan": sim.stats, "plan_options": opts, "plan_seconds": plan_seconds, "final_norm": norm,
-                       "amp_updates_per_s": args.steps * ngates * 2.0 ** n / (total_ms * 1e-3)},
+                       "raw_gates_per_s": raw, "amp_updates_per_s": raw * 2.0 ** n},
             "roofline": {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": 2.0 * shard_bytes, "launches_per_step": passes,
@@ -97,7 +105,7 @@ def run_sharded(args, world, rank, local_rank):
                      "peak_GBps_nominal": 900.0, "frac_of_measured": (nvlink / 770.0) if nvlink else None,
                      "note": "host-timed with a device synchronize on both sides of every swap"},
             "cpu_baseline": None,
-            "e2e": {"value": args.steps * ngates / (total_ms * 1e-3), "unit": "gates/s",
+            "e2e": {"value": raw * 2.0 ** (n - 30), "unit": "gates/s x 2^(n-30)",
                     "h2d_bytes_per_step": 26416 * passes + 64 * n, "d2h_bytes_per_step": 16,
                     "note": "same timed region: set_product + schedule execution through ShardedSimulator.run; "
                             "the state stays sharded on the GPUs (2^n amplitudes exceed host memory), the host reads "
