@@ -362,15 +362,18 @@ class ShardedSimulator:
                         deferred.append(idx)
                         (blocked_diag if is_diag else blocked_full).update(bits)
 
-                def run_ready():
+                def run_ops(indices):
                     segment = []
-                    for idx in ready:
+                    for idx in indices:
                         bits, m, is_diag = ops[idx]
                         p_bits = [phys[b] for b in bits]
                         if is_diag and any(p >= nloc for p in p_bits):
                             p_bits, m = self._restrict_diagonal(p_bits, m)
                         segment.append(([nloc - 1 - p for p in p_bits], m))
                     flush(segment)
+
+                def run_ready():
+                    run_ops(ready)
                     ready.clear()
 
                 if not deferred:
@@ -385,14 +388,16 @@ class ShardedSimulator:
                 for b in bits:
                     if phys[b] < nloc:
                         continue
-                    busy = set()
+                    busy = {}
                     for idx in ready:
                         if not ops[idx][2]:
-                            busy.update(ops[idx][0])
+                            for q in ops[idx][0]:
+                                busy[q] = busy.get(q, 0) + 1
                     local_logical = [l for l in range(st.n) if phys[l] < nloc and l not in bits]
-                    victim = max(local_logical, key=lambda l: (l not in busy, next_use(l, head), phys[l]))
+                    victim = max(local_logical, key=lambda l: (-busy.get(l, 0), next_use(l, head), phys[l]))
                     if victim in busy:
-                        run_ready()
+                        run_ready()       # (running only the closure of the victim's gates was
+                                          #  tried: many small, badly packed plans -- more passes)
                     schedule.append(("swap", phys[b], phys[victim]))
                     phys[b], phys[victim] = phys[victim], phys[b]
                     self.stats["swaps"] += 1
