@@ -81,11 +81,11 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   for (uint64_t t = 0; t < ntiles; ++t) {
     const uint64_t base = qs_tile_base_tab(P, io, t);
     for (int s = 0; s < nsteps; ++s)
-      if (P.steps[s].has_sign) zmask[s] = qs_step_zmask(P, s, base);
+      if (P.steps[s].has_sign) zmask[s] = qs_step_zg(P, s, base);
     if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
       qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io,
-                    [](qs_c128* dst, const qs_c128* src) { *dst = *src; });
+                    [](void* dst, const void* src) { *(qs_c128*)dst = *(const qs_c128*)src; });
     for (int s = 0; s < nsteps; ++s) {
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
         // same variant selection as launch_pass() in kernels.cu

@@ -77,7 +77,7 @@ int bind_device(const void* ptr, DevCtx** ctx) {
 // 16-byte asynchronous global->shared copy (LDGSTS): no register staging, and the
 // thread does not wait, so the next tile streams in while the current one computes.
 struct CopyAsync16 {
-  __device__ __forceinline__ void operator()(qs_c128* dst, const qs_c128* src) const {
+  __device__ __forceinline__ void operator()(void* dst, const void* src) const {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
   }
@@ -139,7 +139,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     qs_c128* nxt = (k & 1u) ? buf0 : buf1;
     const uint64_t base = qs_tile_base_tab(P, s_io, t);
     if ((int)tid < nsteps) {
-      if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zmask(P, (int)tid, base);
+      if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zg(P, (int)tid, base);
     } else if ((int)tid == nsteps && P.fin_has_sign) {
       qs_fin_prepare(P, base, &s_zmask[nsteps], &s_zmask[nsteps + 1]);
     }

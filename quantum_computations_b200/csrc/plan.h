@@ -36,7 +36,7 @@
 
 #define QS_MAX_T        13     // largest tile: 2^13 amplitudes = 128 KiB
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
-#define QS_MAX_STEPS    40
+#define QS_MAX_STEPS    32
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #ifndef QS_THREADS_LOG2
@@ -109,13 +109,18 @@ struct QsStepTab {
   uint16_t jA[16];               // local-index bits of thread-id nibble 0
   uint16_t jB[32];               // local-index bits of thread-id bits 4..8
   uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
-  uint16_t sdep[16];             // swizzled slot offset of amplitude m of a work item
+  uint32_t sdepb[16];            // BYTE offset (swizzled slot * 16) of amplitude m of a work item
+  uint16_t ng[QS_MAX_R];         // copy of QsStep::ng
+  uint16_t qg;                   // bit m: parity of the CZ pairs inside the group for amplitude m
+  uint8_t  gpos[QS_MAX_R];       // copy of QsStep::gpos
+  uint8_t  all_rot;              // QS_STEP_1Q whose members are all QS_FORM_ROT: branch-free fast path
+  uint8_t  pad[3];
 };
 
 // Tables for the load/store phases and the final sign block.
 struct QsIoTab {
-  uint64_t ghi[QS_MAX_ITER];     // global-index bits of iteration i
-  uint16_t shi[QS_MAX_ITER];     // swz(i << QS_THREADS_LOG2)
+  uint64_t gbyte[QS_MAX_ITER];   // BYTE offset in the state of the global-index bits of iteration i
+  uint32_t sbyte[QS_MAX_ITER];   // BYTE offset in the tile of swz(i << QS_THREADS_LOG2)
   uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
   uint32_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
   uint64_t base_tab[4][64];      // tile number -> global index of the tile, 6 bits at a time

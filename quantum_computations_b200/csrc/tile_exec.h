@@ -82,9 +82,9 @@ QS_HD uint32_t qs_fin_neigh(const QsPass& P, uint32_t x) {
 }
 
 // ---- per-launch tables (tile independent) -----------------------------------------------
-// Entry e (0..79) of a step's table: 0..15 -> jA, 16..47 -> jB, 48..63 -> hi,
-// 64..79 -> sdep.
-#define QS_TAB_ENTRIES 80
+// Entry e (0..80) of a step's table: 0..15 -> jA, 16..47 -> jB, 48..63 -> hi,
+// 64..79 -> sdepb, 80 -> the scalar fields.
+#define QS_TAB_ENTRIES 81
 QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint32_t nthr_log2) {
   const QsStep& st = P.steps[s];
   const int nfree = (int)P.T - st.r;
@@ -98,19 +98,38 @@ QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint
   } else if (e < 64) {
     const uint32_t jhi = qs_scatter8((uint32_t)(e - 48), st.fpos + nthr_log2, nfree - lo_bits);
     tab->hi[e - 48] = jhi | (qs_swz(jhi) << 16);
-  } else {
+  } else if (e < 80) {
     // amplitude m: matrix factor f is bit (r-1-f) of m and sits at local position gpos[f]
     const int m = e - 64;
     uint32_t d = 0;
     for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
-    tab->sdep[m] = (uint16_t)qs_swz(d);
+    tab->sdepb[m] = qs_swz(d) << 4;
+  } else {
+    const int r = st.r;
+    uint32_t qg = 0;
+    bool all_rot = st.kind == QS_STEP_1Q;
+    for (int f = 0; f < QS_MAX_R; ++f) {
+      tab->ng[f] = f < r ? st.ng[f] : (uint16_t)0;
+      tab->gpos[f] = f < r ? st.gpos[f] : (uint8_t)0;
+      if (f < r && st.form[f] != QS_FORM_ROT) all_rot = false;
+    }
+    for (int m = 0; m < (1 << r); ++m) {
+      uint32_t q = 0;
+      for (int f = 0; f < r; ++f)
+        if ((m >> (r - 1 - f)) & 1)
+          for (int f2 = f + 1; f2 < r; ++f2)
+            if ((m >> (r - 1 - f2)) & 1) q ^= ((uint32_t)st.ng[f] >> st.gpos[f2]) & 1u;
+      qg |= q << m;
+    }
+    tab->qg = (uint16_t)qg;
+    tab->all_rot = all_rot ? 1 : 0;
   }
 }
 
 QS_HD void qs_build_io_tab(const QsPass& P, uint32_t i, QsIoTab* io, uint32_t nthr_log2) {
   const uint32_t jhi = i << nthr_log2;
-  io->ghi[i] = (P.T <= nthr_log2) ? 0ull : qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2));
-  io->shi[i] = (uint16_t)qs_swz(jhi & ((1u << P.T) - 1u));
+  io->gbyte[i] = ((P.T <= nthr_log2) ? 0ull : qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2))) << 4;
+  io->sbyte[i] = qs_swz(jhi & ((1u << P.T) - 1u)) << 4;
   io->fin_neigh[i] = 0;
   if (P.fin_has_sign && jhi < (1u << P.T)) io->fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
 }
@@ -129,13 +148,16 @@ QS_HD uint32_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
 }
 
 // ---- per-tile sign data ---------------------------------------------------------------------
-// Step s: linear mask z over local positions (only the group bits matter).
-QS_HD uint32_t qs_step_zmask(const QsPass& P, int s, uint64_t base) {
+// Step s: Z's on the group bits for this tile, in m-space (bit r-1-f <-> factor f):
+// local Z gates plus CZ's whose other bit is an outer bit that is 1 in this tile.
+QS_HD uint32_t qs_step_zg(const QsPass& P, int s, uint64_t base) {
   const QsStep& st = P.steps[s];
   const uint8_t* pr = P.pairs + 2 * (uint32_t)st.pair_off;
   uint32_t z = st.zconst;
   for (int i = 0; i < st.n_lo; ++i, pr += 2) z ^= (uint32_t)((base >> pr[1]) & 1ull) << pr[0];
-  return z;
+  uint32_t zg = 0;
+  for (int f = 0; f < st.r; ++f) zg |= ((z >> st.gpos[f]) & 1u) << (st.r - 1 - f);
+  return zg;
 }
 // Final block: tile-uniform bit g and linear mask z.
 QS_HD void qs_fin_prepare(const QsPass& P, uint64_t base, uint32_t* zmask, uint32_t* gsign) {
@@ -163,11 +185,11 @@ QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
 template <class Copy>
 QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, uint64_t base, uint32_t tid,
                          uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, Copy copy) {
-  const uint32_t nthr = 1u << nthr_log2;
-  const uint32_t size = 1u << P.T;
-  const uint32_t slo = qs_swz(tid);
-  const uint64_t b0 = base | glo;
-  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) copy(tile + (slo ^ io.shi[i]), state + (b0 | io.ghi[i]));
+  const uint32_t niter = P.T > nthr_log2 ? 1u << (P.T - nthr_log2) : (tid < (1u << P.T) ? 1u : 0u);
+  const uint32_t slob = qs_swz(tid) << 4;
+  const char* g0 = reinterpret_cast<const char*>(state) + ((base | glo) << 4);   // disjoint bits: | == +
+  char* t0 = reinterpret_cast<char*>(tile);
+  for (uint32_t i = 0; i < niter; ++i) copy(t0 + (slob ^ io.sbyte[i]), g0 + io.gbyte[i]);
 }
 
 // ---- phase: shared -> global, with the pass's final sign block ---------------
@@ -175,22 +197,23 @@ QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, u
 QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile, uint64_t base, uint32_t tid,
                           uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, uint32_t fin_qlo,
                           uint32_t zmask, uint32_t gsign) {
-  const uint32_t nthr = 1u << nthr_log2;
-  const uint32_t size = 1u << P.T;
-  const uint32_t slo = qs_swz(tid);
-  const uint64_t b0 = base | glo;
+  const uint32_t niter = P.T > nthr_log2 ? 1u << (P.T - nthr_log2) : (tid < (1u << P.T) ? 1u : 0u);
+  const uint32_t slob = qs_swz(tid) << 4;
+  char* g0 = reinterpret_cast<char*>(state) + ((base | glo) << 4);
+  const char* t0 = reinterpret_cast<const char*>(tile);
   if (!P.fin_has_sign) {
-    for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) state[b0 | io.ghi[i]] = tile[slo ^ io.shi[i]];
+    for (uint32_t i = 0; i < niter; ++i)
+      *reinterpret_cast<qs_c128*>(g0 + io.gbyte[i]) = *reinterpret_cast<const qs_c128*>(t0 + (slob ^ io.sbyte[i]));
     return;
   }
   // j = tid | (i << nthr_log2):  g + z.j + Q(tid) + Q(jhi) + B(tid, jhi)
   const uint32_t qlo = gsign ^ fin_qlo ^ qs_par(tid & zmask);
   const uint32_t zhi = zmask >> nthr_log2;
-  for (uint32_t i = 0, j = tid; j < size; ++i, j += nthr) {
+  for (uint32_t i = 0; i < niter; ++i) {
     const uint32_t q = qlo ^ qs_par(i & zhi) ^ ((io.fin_q >> i) & 1u) ^ qs_par(tid & io.fin_neigh[i]);
-    qs_c128 v = tile[slo ^ io.shi[i]];
+    qs_c128 v = *reinterpret_cast<const qs_c128*>(t0 + (slob ^ io.sbyte[i]));
     qs_flip(v, q << 31);
-    state[b0 | io.ghi[i]] = v;
+    *reinterpret_cast<qs_c128*>(g0 + io.gbyte[i]) = v;
   }
 }
 
@@ -238,59 +261,38 @@ QS_HD void qs_mat2_rot(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
 // parity(m & W) + qg(m) with W_f = z_f + parity(j0 & ng[f])   (plan.h).
 template <int R, bool DENSE>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                         uint32_t zmask, const QsStepTab& tab, int debug_skip = 0) {
+                         uint32_t zg, const QsStepTab& tab, int debug_skip = 0) {
   const QsStep& st = P.steps[s];
   const uint32_t nwork = 1u << (P.T - R);
   const uint32_t nthr = 1u << nthr_log2;
   const bool has_sign = st.has_sign != 0;
   constexpr int NA = 1 << R;
 
-  uint32_t sdep[NA];                       // swizzled slot offset of amplitude m
-  uint32_t ng[R];                          // in-tile partners of group factor f
-  uint32_t zg = 0;                         // Z on the group bits, in m-space
-  uint32_t qg = 0;                         // bit m: pairs inside the group
+  uint32_t sdb[NA];                        // byte offset of amplitude m inside the tile (swizzled)
 #pragma unroll
-  for (int m = 0; m < NA; ++m) sdep[m] = tab.sdep[m];
-  if (has_sign) {
-    uint32_t gp[R];
+  for (int m = 0; m < NA; ++m) sdb[m] = tab.sdepb[m];
+  uint32_t ng[R];                          // in-tile CZ partners of group factor f
 #pragma unroll
-    for (int f = 0; f < R; ++f) {
-      gp[f] = st.gpos[f];
-      ng[f] = (uint32_t)st.ng[f];
-      zg |= ((zmask >> gp[f]) & 1u) << (R - 1 - f);
-    }
-#pragma unroll
-    for (int m = 0; m < NA; ++m) {
-      uint32_t q = 0;
-#pragma unroll
-      for (int f = 0; f < R; ++f)
-        if ((m >> (R - 1 - f)) & 1) {
-#pragma unroll
-          for (int f2 = f + 1; f2 < R; ++f2)
-            if ((m >> (R - 1 - f2)) & 1) q ^= (ng[f] >> gp[f2]) & 1u;
-        }
-      qg |= q << m;
-    }
-  } else {
-#pragma unroll
-    for (int f = 0; f < R; ++f) ng[f] = 0;
-  }
+  for (int f = 0; f < R; ++f) ng[f] = has_sign ? (uint32_t)tab.ng[f] : 0u;
+  const uint32_t qg = tab.qg;              // bit m: pairs inside the group
+  const bool all_rot = tab.all_rot != 0;
 
   const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
   const uint32_t slo = qs_swz(jlo);
+  char* const t0 = reinterpret_cast<char*>(tile);
 
   for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthr) {
     const uint32_t hi = tab.hi[i];
     const uint32_t j0 = jlo | (hi & 0xffffu);
-    const uint32_t s0 = slo ^ (hi >> 16);
+    const uint32_t s0b = (slo ^ (hi >> 16)) << 4;
     qs_c128 a[NA];
 #pragma unroll
-    for (int m = 0; m < NA; ++m) a[m] = tile[s0 ^ sdep[m]];
+    for (int m = 0; m < NA; ++m) a[m] = *reinterpret_cast<const qs_c128*>(t0 + (s0b ^ sdb[m]));
     if (has_sign) {
+      // W_f = z_f + parity(j0 & ng[f]); sign bit of amplitude m = qg_m ^ parity(m & W)
       uint32_t W = zg;
 #pragma unroll
       for (int f = 0; f < R; ++f) W ^= qs_par(j0 & ng[f]) << (R - 1 - f);
-      // signs of all 2^R amplitudes at once: bit m = qg_m ^ parity(m & W)
       uint32_t sg = qg;
 #pragma unroll
       for (int b = 0; b < R; ++b) {
@@ -300,11 +302,28 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
         sg ^= (0u - ((W >> b) & 1u)) & pat;
       }
 #pragma unroll
-      for (int m = 0; m < NA; ++m) qs_flip(a[m], (sg >> m) << 31);
+      for (int m = 0; m < NA; ++m) qs_flip(a[m], (sg << (31 - m)) & 0x80000000u);
     }
-    if (debug_skip & 4) {            // development: shared-memory round trip without the math
+    if (debug_skip & 4) {
+      // development: shared-memory round trip without the math
+    } else if (all_rot) {
+      // branch-free fast path: phase table, then one real rotation per group bit
+      const double* ph = P.coef + st.ph_off;
 #pragma unroll
-      for (int m = 0; m < NA; ++m) tile[s0 ^ sdep[m]] = a[m];
+      for (int m = 0; m < NA; ++m) {
+        const double pr = ph[2 * m], pi = ph[2 * m + 1];
+        const double x = a[m].x, y = a[m].y;
+        a[m].x = pr * x - pi * y;
+        a[m].y = pr * y + pi * x;
+      }
+#pragma unroll
+      for (int f = 0; f < R; ++f) {
+        const double* mat = P.coef + st.coef_off + 8 * f;
+        const int bit = 1 << (R - 1 - f);
+#pragma unroll
+        for (int m = 0; m < NA; ++m)
+          if (!(m & bit)) qs_mat2_rot(mat, a[m], a[m | bit]);
+      }
     } else if (!DENSE || st.kind == QS_STEP_1Q) {
       if (st.has_phase) {
         const double* ph = P.coef + st.ph_off;
@@ -316,31 +335,50 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           a[m].y = pr * y + pi * x;
         }
       }
-#pragma unroll
-      for (int f = 0; f < R; ++f) {
+#pragma unroll 1
+      for (int f = 0; f < R; ++f) {        // rolled: the mixed-form path is rare, keep it small
         const double* mat = P.coef + st.coef_off + 8 * f;
-        const int bit = 1 << (R - 1 - f);
         const uint32_t form = st.form[f];
-        if (form == QS_FORM_GENERAL) {
+        // pairs along factor f (f is a run-time value here): enumerate with a switch so
+        // that the amplitude indices stay compile-time constants
+        if (R >= 1 && f == 0) {
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (!(m & bit)) qs_mat2(mat, a[m], a[m | bit]);
-        } else if (form == QS_FORM_ROT) {
+            if (!(m & (1 << (R - 1)))) {
+              if (form == QS_FORM_GENERAL) qs_mat2(mat, a[m], a[m | (1 << (R - 1))]);
+              else if (form == QS_FORM_ROT) qs_mat2_rot(mat, a[m], a[m | (1 << (R - 1))]);
+              else if (form == QS_FORM_DIAG) qs_mat2_diag(mat, a[m], a[m | (1 << (R - 1))]);
+              else qs_mat2_anti(mat, a[m], a[m | (1 << (R - 1))]);
+            }
+        } else if (R >= 2 && f == 1) {
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (!(m & bit)) qs_mat2_rot(mat, a[m], a[m | bit]);
-        } else if (form == QS_FORM_DIAG) {
+            if (!(m & (1 << (R >= 2 ? R - 2 : 0)))) {
+              if (form == QS_FORM_GENERAL) qs_mat2(mat, a[m], a[m | (1 << (R >= 2 ? R - 2 : 0))]);
+              else if (form == QS_FORM_ROT) qs_mat2_rot(mat, a[m], a[m | (1 << (R >= 2 ? R - 2 : 0))]);
+              else if (form == QS_FORM_DIAG) qs_mat2_diag(mat, a[m], a[m | (1 << (R >= 2 ? R - 2 : 0))]);
+              else qs_mat2_anti(mat, a[m], a[m | (1 << (R >= 2 ? R - 2 : 0))]);
+            }
+        } else if (R >= 3 && f == 2) {
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (!(m & bit)) qs_mat2_diag(mat, a[m], a[m | bit]);
-        } else {
+            if (!(m & (1 << (R >= 3 ? R - 3 : 0)))) {
+              if (form == QS_FORM_GENERAL) qs_mat2(mat, a[m], a[m | (1 << (R >= 3 ? R - 3 : 0))]);
+              else if (form == QS_FORM_ROT) qs_mat2_rot(mat, a[m], a[m | (1 << (R >= 3 ? R - 3 : 0))]);
+              else if (form == QS_FORM_DIAG) qs_mat2_diag(mat, a[m], a[m | (1 << (R >= 3 ? R - 3 : 0))]);
+              else qs_mat2_anti(mat, a[m], a[m | (1 << (R >= 3 ? R - 3 : 0))]);
+            }
+        } else if (R >= 4 && f == 3) {
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (!(m & bit)) qs_mat2_anti(mat, a[m], a[m | bit]);
+            if (!(m & 1)) {
+              if (form == QS_FORM_GENERAL) qs_mat2(mat, a[m], a[m | 1]);
+              else if (form == QS_FORM_ROT) qs_mat2_rot(mat, a[m], a[m | 1]);
+              else if (form == QS_FORM_DIAG) qs_mat2_diag(mat, a[m], a[m | 1]);
+              else qs_mat2_anti(mat, a[m], a[m | 1]);
+            }
         }
       }
-#pragma unroll
-      for (int m = 0; m < NA; ++m) tile[s0 ^ sdep[m]] = a[m];
     } else {
       // dense 2^R x 2^R matrix: inputs are all in registers, so rows can be
       // written back one at a time (rolled loop keeps the code small)
@@ -355,9 +393,12 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           im += mr * a[c].y + mi * a[c].x;
         }
         qs_c128 o; o.x = re; o.y = im;
-        tile[s0 ^ tab.sdep[row]] = o;
+        *reinterpret_cast<qs_c128*>(t0 + (s0b ^ tab.sdepb[row])) = o;
       }
+      continue;
     }
+#pragma unroll
+    for (int m = 0; m < NA; ++m) *reinterpret_cast<qs_c128*>(t0 + (s0b ^ sdb[m])) = a[m];
   }
 }
 
