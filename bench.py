@@ -170,7 +170,7 @@ def run_reference(args):
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
             "data": "synthetic",
             "config": {"workload": "C4 generator (sv_random_circuit, depth 200, seed 30) run by the reference's "
                                    "dense-operator algorithm at N=12; it cannot hold N=30"},
@@ -287,7 +287,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": f"C4: {n}-qubit complex128 random circuit, depth {args.depth}, "
                                    f"{ngates} gates (sv_random_circuit seed {args.seed}); state 2^{n} x 16 B "
                                    "exceeds L2, no flush needed",

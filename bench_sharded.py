@@ -90,7 +90,7 @@ def run_sharded(args, world, rank, local_rank):
             "metric": METRIC, "value": raw * 2.0 ** (n - 30), "unit": "gates/s",
             "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": f"C5: {n}-qubit complex128 random circuit, depth {args.depth}, {ngates} gates, "
                                    f"sharded over {world} GPUs by the top {g} qubits ({state.n_local} local qubits, "
                                    f"{shard_bytes / 2 ** 30:.0f} GiB per GPU); shards exceed L2, no flush needed",
