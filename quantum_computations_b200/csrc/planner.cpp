@@ -281,45 +281,6 @@ uint8_t mat_form(const Op& op) {
   return QS_FORM_GENERAL;
 }
 
-typedef std::vector<std::pair<uint8_t, uint8_t>> PairList;
-constexpr int kMaxPend = 640;
-
-// Final sign block of a pass: every pair of `pairs` (global bit numbers), applied
-// while the tile is written back.  Appends to the pass's pair array.
-void write_final_block(QsPass& P, const PairList& pairs) {
-  int lpos[64];
-  for (int b = 0; b < 64; ++b) lpos[b] = -1;
-  for (uint32_t l = 0; l < P.T; ++l) lpos[P.tile_bits[l]] = (int)l;
-  int npairs = (int)P.npairs;
-  uint8_t* dst = P.pairs + 2 * npairs;
-  int w = 0, n_oo = 0, n_lo = 0;
-  for (const auto& pr : pairs)
-    if (lpos[pr.first] < 0 && lpos[pr.second] < 0) { dst[w++] = pr.first; dst[w++] = pr.second; ++n_oo; }
-  for (const auto& pr : pairs) {
-    const int a = pr.first, b = pr.second;
-    if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
-      const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
-      dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
-    }
-  }
-  for (const auto& pr : pairs) {
-    const int a = pr.first, b = pr.second;
-    if (lpos[a] >= 0 && lpos[b] >= 0) {
-      if (a == b) {
-        P.fin_zconst ^= (uint16_t)(1u << lpos[a]);
-      } else {
-        P.fin_nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
-        P.fin_nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
-      }
-    }
-  }
-  P.fin_has_sign = pairs.empty() ? 0 : 1;
-  P.fin_pair_off = (uint16_t)npairs;
-  P.fin_n_oo = (uint16_t)n_oo;
-  P.fin_n_lo = (uint16_t)n_lo;
-  P.npairs = (uint32_t)(npairs + n_oo + n_lo);
-}
-
 // 8-double coefficient slot of one member of a 1Q step
 void write_1q_slot(double* dst, const Op& op) {
   if (op.rot) {
@@ -343,8 +304,7 @@ struct Walker {
   // tile is the bit set S.  With `pass` == nullptr only the score is computed
   // (and at most opt.lookahead pending ops are visited).
   // Returns dense_taken * 4096 + min(sign_taken, 4095).
-  long walk(size_t first, uint64_t S, QsPass* pass, std::vector<size_t>* taken_idx,
-            const PairList* carry_in = nullptr, PairList* carry_out = nullptr) const {
+  long walk(size_t first, uint64_t S, QsPass* pass, std::vector<size_t>* taken_idx) const {
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     uint64_t blocked_full = 0, blocked_diag = 0;
     int dense_taken = 0, sign_taken = 0, visited = 0;
@@ -364,17 +324,9 @@ struct Walker {
     for (int b = 0; b < 64; ++b) { last_dense[b] = -1; last_sign[b] = 0; }
     // Sign pairs taken but not yet attached: each waits for the first later step
     // whose group contains one of its bits, else for the pass's final block.
-    // Pairs left over by the previous pass of the plan arrive in `carry_in`; what is
-    // left at the end of this pass goes to `carry_out` (only the last pass of a plan
-    // applies leftovers, on its way back to HBM).
     uint64_t pend_mask = 0;
-    uint8_t pend[kMaxPend][2];
+    uint8_t pend[256][2];
     int npend = 0;
-    if (carry_in)
-      for (const auto& pr : *carry_in) {
-        pend[npend][0] = pr.first; pend[npend][1] = pr.second; ++npend;
-        pend_mask |= (1ull << pr.first) | (1ull << pr.second);
-      }
 
     // (local position, outer bit) pairs per step; flattened into QsPass::pairs at the end
     constexpr int kMaxLo = 24;
@@ -447,7 +399,7 @@ struct Walker {
       const Op& op = ops[i];
       const uint64_t m = masks[i];
       if (op.kind == OP_SIGN) {
-        const bool room = total_lo + npend + 1 <= QS_MAX_PAIRS && npend < kMaxPend - 2;
+        const bool room = total_lo + npend + 1 <= QS_MAX_PAIRS && npend < 250;
         if ((m & blocked_full) == 0 && room) {
           // CZ is an involution: a repeated pending pair cancels
           const int a = std::min(op.bits[0], op.bits[1]), b = std::max(op.bits[0], op.bits[1]);
@@ -577,14 +529,39 @@ struct Walker {
           ++npairs;
         }
       }
-      pass->npairs = (uint32_t)npairs;
-      PairList left;
-      for (int p = 0; p < npend; ++p) left.emplace_back(pend[p][0], pend[p][1]);
-      if (carry_out) *carry_out = left;            // the caller decides where they are applied
-      else write_final_block(*pass, left);
-      npairs = (int)pass->npairs;
+      // whatever is still pending goes into the final block
+      uint8_t* dst = pass->pairs + 2 * npairs;
+      int w = 0, n_oo = 0, n_lo = 0;
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if (lpos[a] < 0 && lpos[b] < 0) { dst[w++] = (uint8_t)a; dst[w++] = (uint8_t)b; ++n_oo; }
+      }
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
+          const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
+          dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
+        }
+      }
+      for (int p = 0; p < npend; ++p) {
+        const int a = pend[p][0], b = pend[p][1];
+        if (lpos[a] >= 0 && lpos[b] >= 0) {
+          if (a == b) {
+            pass->fin_zconst ^= (uint16_t)(1u << lpos[a]);
+          } else {
+            pass->fin_nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
+            pass->fin_nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
+          }
+        }
+      }
+      pass->fin_has_sign = npend > 0 ? 1 : 0;
+      pass->fin_pair_off = (uint16_t)npairs;
+      pass->fin_n_oo = (uint16_t)n_oo;
+      pass->fin_n_lo = (uint16_t)n_lo;
+      npairs += n_oo + n_lo;
       pass->nsteps = (uint32_t)nsteps;
       pass->ncoef = (uint32_t)ncoef;
+      pass->npairs = (uint32_t)npairs;
     }
     return (long)dense_taken * 4096 + std::min(sign_taken, 4095);
   }
@@ -666,25 +643,12 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
 
   // first pending dense op per bit (tie-break when growing the tile)
   size_t first = 0;
-  PairList carry;                       // sign pairs handed from pass to pass
-  auto sign_only_pass = [&]() {         // apply the carried pairs now (before a generic gate)
-    PlanItem it;
-    it.generic = false;
-    memset(&it.pass, 0, sizeof(it.pass));
-    it.pass.T = (uint32_t)T;
-    for (int l = 0; l < T; ++l) it.pass.tile_bits[l] = (uint8_t)l;
-    write_final_block(it.pass, carry);
-    carry.clear();
-    stats.n_passes++;
-    out->items.push_back(std::move(it));
-  };
   while (true) {
     while (first < ops.size() && done[first]) ++first;
     if (first >= ops.size()) break;
 
     const Op& head = ops[first];
     if (head.kind == OP_DENSE && head.k > QS_MAX_R) {
-      if (!carry.empty()) sign_only_pass();
       PlanItem it;
       it.generic = true;
       it.op = head;
@@ -718,7 +682,7 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
         int best_bit = -1;
         for (int b = 0; b < n; ++b) {
           if (S >> b & 1) continue;
-          const long sc = wk.walk(first, S | (1ull << b), nullptr, nullptr, &carry, nullptr);
+          const long sc = wk.walk(first, S | (1ull << b), nullptr, nullptr);
           if (sc > best_score ||
               (sc == best_score && best_bit >= 0 && next_dense[b] < next_dense[best_bit])) {
             best_score = sc;
@@ -741,23 +705,10 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
         if (S >> b & 1) P.tile_bits[l++] = (uint8_t)b;
     }
     std::vector<size_t> taken;
-    PairList left;
-    wk.walk(first, S, &P, &taken, &carry, &left);
+    wk.walk(first, S, &P, &taken);
     if (taken.empty())
       return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
     for (size_t idx : taken) done[idx] = 1;
-    {
-      // leftovers ride on to the next pass; the last pass of the plan (or an
-      // overfull list) applies them while storing
-      size_t nxt = first;
-      while (nxt < ops.size() && done[nxt]) ++nxt;
-      const bool last = nxt >= ops.size();
-      if (last || left.size() > (size_t)(kMaxPend - 140)) {
-        write_final_block(P, left);
-        left.clear();
-      }
-      carry.swap(left);
-    }
     assign_runs(P);
     for (uint32_t s = 0; s < P.nsteps; ++s) {
       QsStep& st = P.steps[s];
