@@ -90,7 +90,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // `dbuf` the dynamic shared memory holds two tile buffers and the loads of tile
 // k+1 are issued before the steps of tile k run.
 template <int MAXR, bool DENSE>
-__global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1) : (MAXR <= 3 ? 3 : 2)))
+__global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1)
+                                               : QS_THREADS_LOG2 <= 7 ? 3 : (MAXR <= 3 ? 3 : 2)))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf,
             unsigned* sm_arrival, int stagger_cycles, int occ, int debug_skip) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
@@ -107,7 +108,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
   if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
   if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
-  if (tid < 256) qs_build_base_tab(P, tid, &s_io);
+  for (uint32_t e = tid; e < 256; e += QS_THREADS) qs_build_base_tab(P, e, &s_io);
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
   const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
   const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;

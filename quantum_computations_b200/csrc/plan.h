@@ -34,15 +34,17 @@
 #pragma once
 #include <stdint.h>
 
-#define QS_MAX_T        13     // largest tile: 2^13 amplitudes = 128 KiB
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
 #define QS_MAX_STEPS    32
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #ifndef QS_THREADS_LOG2
-#define QS_THREADS_LOG2 8      // threads per CTA = 256 (9 = 512 is an experiment switch)
+#define QS_THREADS_LOG2 8      // threads per CTA = 256 (7 and 9 are experiment switches)
 #endif
+// largest tile: 2^13 amplitudes = 128 KiB; a step's per-thread iteration table has 16 entries
+#define QS_MAX_T        (QS_THREADS_LOG2 + 5 < 13 ? QS_THREADS_LOG2 + 5 : 13)
 #define QS_THREADS      (1 << QS_THREADS_LOG2)
+#define QS_WARP_BITS    (QS_THREADS_LOG2 - 5)                 // thread-id bits that select the warp
 #define QS_MAX_ITER     (1 << (QS_MAX_T - QS_THREADS_LOG2))   // amplitudes per thread in load/store
 
 enum QsStepKind : uint8_t {
@@ -122,6 +124,6 @@ struct QsIoTab {
   uint64_t gbyte[QS_MAX_ITER];   // BYTE offset in the state of the global-index bits of iteration i
   uint32_t sbyte[QS_MAX_ITER];   // BYTE offset in the tile of swz(i << QS_THREADS_LOG2)
   uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
-  uint32_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
+  uint64_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
   uint64_t base_tab[4][64];      // tile number -> global index of the tile, 6 bits at a time
 };

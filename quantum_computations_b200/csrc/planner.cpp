@@ -605,7 +605,7 @@ void assign_runs(QsPass& P) {
       const QsStep& st = P.steps[e];
       for (int f = 0; f < st.r; ++f) u |= 1u << st.gpos[f];
       const int r = std::max(maxr, (int)st.r);
-      if (T - __builtin_popcount(u) < 3 || T - r < QS_THREADS_LOG2) break;
+      if (T - __builtin_popcount(u) < QS_WARP_BITS || T - r < QS_THREADS_LOG2) break;
       used = u;
       maxr = r;
       ++e;
@@ -616,11 +616,11 @@ void assign_runs(QsPass& P) {
       ++s;
       continue;
     }
-    int wp[3], nw = 0;
-    for (int p = T - 1; p >= 0 && nw < 3; --p)
+    int wp[4], nw = 0;
+    for (int p = T - 1; p >= 0 && nw < QS_WARP_BITS; --p)
       if (!(used >> p & 1)) wp[nw++] = p;
     for (int i = s; i < e; ++i) {
-      order_free_positions(P.steps[i], T, wp, 3);
+      order_free_positions(P.steps[i], T, wp, QS_WARP_BITS);
       P.steps[i].block_sync = (i == e - 1) ? 1 : 0;
     }
     s = e;

@@ -137,12 +137,12 @@ QS_HD void qs_build_base_tab(const QsPass& P, uint32_t e, QsIoTab* io) {   // e 
   io->base_tab[e >> 6][e & 63u] = qs_tile_base(P, (uint64_t)(e & 63u) << (6 * (e >> 6)));
 }
 // fin_q is a bit mask over i; build it with one thread (or sequentially on the host)
-QS_HD uint32_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
-  uint32_t q = 0;
+QS_HD uint64_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
+  uint64_t q = 0;
   if (!P.fin_has_sign) return 0;
   for (uint32_t i = 0; i < QS_MAX_ITER; ++i) {
     const uint32_t jhi = i << nthr_log2;
-    if (jhi < (1u << P.T)) q |= qs_fin_quad(P, jhi) << i;
+    if (jhi < (1u << P.T)) q |= (uint64_t)qs_fin_quad(P, jhi) << i;
   }
   return q;
 }
@@ -210,7 +210,7 @@ QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile, 
   const uint32_t qlo = gsign ^ fin_qlo ^ qs_par(tid & zmask);
   const uint32_t zhi = zmask >> nthr_log2;
   for (uint32_t i = 0; i < niter; ++i) {
-    const uint32_t q = qlo ^ qs_par(i & zhi) ^ ((io.fin_q >> i) & 1u) ^ qs_par(tid & io.fin_neigh[i]);
+    const uint32_t q = qlo ^ qs_par(i & zhi) ^ (uint32_t)((io.fin_q >> i) & 1ull) ^ qs_par(tid & io.fin_neigh[i]);
     qs_c128 v = *reinterpret_cast<const qs_c128*>(t0 + (slob ^ io.sbyte[i]));
     qs_flip(v, q << 31);
     *reinterpret_cast<qs_c128*>(g0 + io.gbyte[i]) = v;

@@ -24,5 +24,6 @@ def cuda_backend():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from quantum_computations_b200 import engine
+    from quantum_computations_b200 import build_native, engine
+    build_native.build_cuda()          # no-op when csrc/libqsim_b200.so is up to date
     return engine.get_backend()
