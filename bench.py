@@ -275,7 +275,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / e2e_steps
             assert abs(np.vdot(out[:1 << 20], out[:1 << 20]).real) >= 0.0
-            h2d = passes * 26256 + 64 * n                       # kernel-parameter blocks + product-state amplitudes
+            h2d = passes * 25288 + 64 * n                       # kernel-parameter blocks + product-state amplitudes
             e2e = {"value": ngates / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": need,
                    "seconds_per_step": dt, "steps": e2e_steps}
         else:

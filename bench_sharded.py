@@ -108,7 +108,7 @@ def run_sharded(args, world, rank, local_rank):
                      "note": "host-timed with a device synchronize on both sides of every swap"},
             "cpu_baseline": None,
             "e2e": {"value": raw * 2.0 ** (n - 30), "unit": "gates/s",
-                    "h2d_bytes_per_step": 26256 * passes + 64 * n, "d2h_bytes_per_step": 16,
+                    "h2d_bytes_per_step": 25288 * passes + 64 * n, "d2h_bytes_per_step": 16,
                     "note": "same timed region: set_product + schedule execution through ShardedSimulator.run; "
                             "the state stays sharded on the GPUs (2^n amplitudes exceed host memory), the host reads "
                             "back the norm"},

@@ -25,13 +25,12 @@ int64_t g_launches = 0;
 // of shared-memory slots.
 int g_ownership_violations = 0;
 
-void slots_of_step(const QsPass& P, int s, const QsStepTid& ttab, std::vector<int>& owner) {
-  const QsStepUni& tab = P.uni[s];
+void slots_of_step(const QsPass& P, int s, const QsStepTab& tab, std::vector<int>& owner) {
   const QsStep& st = P.steps[s];
   const uint32_t nwork = 1u << (P.T - st.r);
   owner.assign((size_t)1 << P.T, -1);
   for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
-    const uint32_t jlo = (uint32_t)ttab.jA[tid & 15u] | (uint32_t)ttab.jB[(tid >> 4) & 31u];
+    const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
     for (uint32_t i = 0, w = tid; w < nwork; ++i, w += QS_THREADS) {
       const uint32_t j0 = jlo | (tab.hi[i] & 0xffffu);
       for (int m = 0; m < (1 << st.r); ++m) {
@@ -43,7 +42,7 @@ void slots_of_step(const QsPass& P, int s, const QsStepTid& ttab, std::vector<in
   }
 }
 
-void check_warp_ownership(const QsPass& P, int s, const QsStepTid& tab_s) {
+void check_warp_ownership(const QsPass& P, int s, const QsStepTab& tab_s) {
   static std::vector<int> prev;
   static int prev_step = -2;
   static const QsPass* prev_pass = nullptr;
@@ -62,12 +61,16 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   const int nsteps = (int)P.nsteps;
   std::vector<qs_c128> tile((size_t)1 << P.T);
   std::vector<uint32_t> zmask(nsteps + 2, 0);
-  std::vector<QsStepTid> tab(nsteps ? nsteps : 1);
+  std::vector<QsStepTab> tab(nsteps ? nsteps : 1);
+  QsIoTab io;
   bool dense = false;
   for (int s = 0; s < nsteps; ++s) {
     dense |= P.steps[s].kind == QS_STEP_DENSE;
-    for (int e = 0; e < QS_TID_ENTRIES; ++e) qs_build_step_tid(P, s, e, &tab[s], QS_THREADS_LOG2);
+    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
   }
+  for (uint32_t i = 0; i < QS_MAX_ITER; ++i) qs_build_io_tab(P, i, &io, QS_THREADS_LOG2);
+  io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  for (uint32_t e = 0; e < 256; ++e) qs_build_base_tab(P, e, &io);
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
   std::vector<uint64_t> glo(QS_THREADS);
   std::vector<uint32_t> fin_qlo(QS_THREADS);
@@ -76,12 +79,12 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
     fin_qlo[tid] = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   }
   for (uint64_t t = 0; t < ntiles; ++t) {
-    const uint64_t base = qs_tile_base_tab(P, t);
+    const uint64_t base = qs_tile_base_tab(P, io, t);
     for (int s = 0; s < nsteps; ++s)
       if (P.steps[s].has_sign) zmask[s] = qs_step_zg(P, s, base);
     if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid],
+      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io,
                     [](void* dst, const void* src) { *(qs_c128*)dst = *(const qs_c128*)src; });
     for (int s = 0; s < nsteps; ++s) {
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
@@ -92,7 +95,7 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
       if (t == 0) check_warp_ownership(P, s, tab[s]);
     }
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], fin_qlo[tid],
+      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io, fin_qlo[tid],
                      zmask[nsteps], zmask[nsteps + 1]);
   }
   ++g_launches;

@@ -97,15 +97,18 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
   qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
-  __shared__ QsStepTid s_tab[QS_MAX_STEPS];
+  __shared__ QsStepTab s_tab[QS_MAX_STEPS];
+  __shared__ QsIoTab s_io;
   __shared__ uint32_t s_zmask[QS_MAX_STEPS + 2];   // [nsteps], then final z, final g
   const uint32_t tid = threadIdx.x;
   const int nsteps = (int)P.nsteps;
 
-  // thread-id indexed tables, once per launch (the grid is persistent); everything
-  // indexed by a uniform value comes precomputed inside P
-  for (int e = (int)tid; e < nsteps * QS_TID_ENTRIES; e += QS_THREADS)
-    qs_build_step_tid(P, e / QS_TID_ENTRIES, e % QS_TID_ENTRIES, &s_tab[e / QS_TID_ENTRIES], QS_THREADS_LOG2);
+  // tile-independent tables, once per launch (the grid is persistent)
+  for (int e = (int)tid; e < nsteps * QS_TAB_ENTRIES; e += QS_THREADS)
+    qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
+  if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
+  if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
+  for (uint32_t e = tid; e < 256; e += QS_THREADS) qs_build_base_tab(P, e, &s_io);
   const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
   const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
   const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
@@ -129,13 +132,13 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
 
   uint64_t t = blockIdx.x;
   if (dbuf && t < ntiles)
-    qs_phase_load(P, state, buf0, qs_tile_base_tab(P, t), tid, QS_THREADS_LOG2, glo, CopyAsync16());
+    qs_phase_load(P, state, buf0, qs_tile_base_tab(P, s_io, t), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
   cp_async_commit();
 
   for (uint32_t k = 0; t < ntiles; t += gridDim.x, ++k) {
     qs_c128* cur = (dbuf && (k & 1u)) ? buf1 : buf0;
     qs_c128* nxt = (k & 1u) ? buf0 : buf1;
-    const uint64_t base = qs_tile_base_tab(P, t);
+    const uint64_t base = qs_tile_base_tab(P, s_io, t);
     if ((int)tid < nsteps) {
       if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zg(P, (int)tid, base);
     } else if ((int)tid == nsteps && P.fin_has_sign) {
@@ -144,11 +147,11 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
     if (dbuf) {
       const uint64_t tn = t + gridDim.x;
       if (tn < ntiles)
-        qs_phase_load(P, state, nxt, qs_tile_base_tab(P, tn), tid, QS_THREADS_LOG2, glo, CopyAsync16());
+        qs_phase_load(P, state, nxt, qs_tile_base_tab(P, s_io, tn), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
       cp_async_commit();
       cp_async_wait<1>();          // everything but the prefetch just issued has landed
     } else {
-      if (!(debug_skip & 1)) qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, CopyAsync16());
+      if (!(debug_skip & 1)) qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
       cp_async_commit();
       cp_async_wait<0>();
     }
@@ -160,7 +163,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
       else __syncwarp();
     }
     if (!(debug_skip & 2))
-      qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, fin_qlo, s_zmask[nsteps],
+      qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
                      s_zmask[nsteps + 1]);
     __syncthreads();
   }

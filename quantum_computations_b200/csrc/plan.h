@@ -37,7 +37,7 @@
 #define QS_MAX_R        4      // group bits per step (dense 16x16 at most)
 #define QS_MAX_STEPS    32
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
-#define QS_MAX_COEF     2048   // doubles of matrix coefficients per pass
+#define QS_MAX_COEF     2816   // doubles of matrix coefficients per pass
 #ifndef QS_THREADS_LOG2
 #define QS_THREADS_LOG2 8      // threads per CTA = 256 (7 and 9 are experiment switches)
 #endif
@@ -82,36 +82,6 @@ struct QsStep {
   uint16_t ng[QS_MAX_R];         // in-tile CZ partners (local positions) of group factor f
 };
 
-// Lookup tables.  Everything indexed by a warp-uniform value (the per-thread
-// iteration counter, the amplitude number inside a work item, the tile number)
-// is precomputed by the host planner and travels inside QsPass, so the kernel
-// reads it through the uniform datapath (LDCU) and the shared-memory pipe --
-// the busiest unit of the kernel -- only moves amplitudes.  Only the tables
-// indexed by the thread id (QsStepTid) are built in shared memory, once per launch.
-struct QsStepUni {
-  uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
-  uint32_t sdepb[16];            // BYTE offset (swizzled slot * 16) of amplitude m of a work item
-  uint16_t ng[QS_MAX_R];         // copy of QsStep::ng
-  uint16_t qg;                   // bit m: parity of the CZ pairs inside the group for amplitude m
-  uint8_t  gpos[QS_MAX_R];       // copy of QsStep::gpos
-  uint8_t  all_rot;              // QS_STEP_1Q whose members are all QS_FORM_ROT: branch-free fast path
-  uint8_t  pad;
-};
-
-struct QsStepTid {
-  uint16_t jA[16];               // local-index bits of thread-id nibble 0
-  uint16_t jB[32];               // local-index bits of thread-id bits 4..8
-};
-
-// Tables for the load/store phases, the final sign block and the tile base.
-struct QsIoTab {
-  uint64_t gbyte[QS_MAX_ITER];   // BYTE offset in the state of the global-index bits of iteration i
-  uint32_t sbyte[QS_MAX_ITER];   // BYTE offset in the tile of swz(i << QS_THREADS_LOG2)
-  uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
-  uint64_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
-  uint64_t base_tab[4][64];      // tile number -> global index of the tile, 6 bits at a time
-};
-
 struct QsPass {
   uint32_t T;                    // tile bits
   uint32_t nsteps;
@@ -127,8 +97,6 @@ struct QsPass {
   uint16_t fin_zconst;
   uint16_t fin_nsym[QS_MAX_T];   // fin_nsym[p]: local positions CZ-coupled to local position p
   QsStep   steps[QS_MAX_STEPS];
-  QsStepUni uni[QS_MAX_STEPS];   // host-built lookup tables (see above)
-  QsIoTab  io;
   uint8_t  pairs[QS_MAX_PAIRS * 2];
   double   coef[QS_MAX_COEF];
 };
@@ -136,3 +104,26 @@ struct QsPass {
 // CUDA kernel parameters are limited to 32764 bytes (CUDA >= 12.1, sm_70+).
 static_assert(sizeof(QsPass) <= 32000, "QsPass must fit in the kernel parameter space");
 
+// Per-step lookup tables, built once per kernel launch in shared memory (they do
+// not depend on the tile): where the thread id and the per-thread iteration
+// counter land inside the tile.
+struct QsStepTab {
+  uint16_t jA[16];               // local-index bits of thread-id nibble 0
+  uint16_t jB[32];               // local-index bits of thread-id bits 4..8
+  uint32_t hi[16];               // iteration i: jhi | swz(jhi) << 16
+  uint32_t sdepb[16];            // BYTE offset (swizzled slot * 16) of amplitude m of a work item
+  uint16_t ng[QS_MAX_R];         // copy of QsStep::ng
+  uint16_t qg;                   // bit m: parity of the CZ pairs inside the group for amplitude m
+  uint8_t  gpos[QS_MAX_R];       // copy of QsStep::gpos
+  uint8_t  all_rot;              // QS_STEP_1Q whose members are all QS_FORM_ROT: branch-free fast path
+  uint8_t  pad[3];
+};
+
+// Tables for the load/store phases and the final sign block.
+struct QsIoTab {
+  uint64_t gbyte[QS_MAX_ITER];   // BYTE offset in the state of the global-index bits of iteration i
+  uint32_t sbyte[QS_MAX_ITER];   // BYTE offset in the tile of swz(i << QS_THREADS_LOG2)
+  uint16_t fin_neigh[QS_MAX_ITER];  // XOR of fin_nsym over the bits of i << QS_THREADS_LOG2
+  uint64_t fin_q;                // bit i: Q(i << QS_THREADS_LOG2)
+  uint64_t base_tab[4][64];      // tile number -> global index of the tile, 6 bits at a time
+};

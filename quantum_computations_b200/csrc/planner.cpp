@@ -10,7 +10,6 @@
 //   * non-diagonal gates need their qubits inside the tile, so each pass picks
 //     the T tile bits that let it absorb the most pending gates.
 #include "planner.h"
-#include "tile_exec.h"
 
 #include <algorithm>
 #include <cstring>
@@ -711,8 +710,6 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
       return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
     for (size_t idx : taken) done[idx] = 1;
     assign_runs(P);
-    for (uint32_t s = 0; s < P.nsteps; ++s) qs_build_step_uni(P, (int)s, QS_THREADS_LOG2);
-    qs_build_io(P, QS_THREADS_LOG2);
     for (uint32_t s = 0; s < P.nsteps; ++s) {
       QsStep& st = P.steps[s];
       stats.n_steps++;

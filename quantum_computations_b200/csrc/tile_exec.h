@@ -61,8 +61,7 @@ QS_HD uint64_t qs_tile_base(const QsPass& P, uint64_t tile) {
 // The same through the per-launch table (the deposit is OR-linear in the tile
 // number): four lookups instead of a T-step loop.  Tile numbers beyond 24 bits
 // fall back to the loop for the excess.
-QS_HD uint64_t qs_tile_base_tab(const QsPass& P, uint64_t tile) {
-  const QsIoTab& io = P.io;
+QS_HD uint64_t qs_tile_base_tab(const QsPass& P, const QsIoTab& io, uint64_t tile) {
   uint64_t base = io.base_tab[0][tile & 63u] | io.base_tab[1][(tile >> 6) & 63u] |
                   io.base_tab[2][(tile >> 12) & 63u] | io.base_tab[3][(tile >> 18) & 63u];
   if (tile >> 24) base |= qs_tile_base(P, (tile >> 24) << 24);
@@ -83,76 +82,69 @@ QS_HD uint32_t qs_fin_neigh(const QsPass& P, uint32_t x) {
 }
 
 // ---- per-launch tables (tile independent) -----------------------------------------------
-// Thread-id indexed part of a step's tables (built in shared memory by the kernel
-// prologue): entry e in 0..15 -> jA, 16..47 -> jB.
-#define QS_TID_ENTRIES 48
-QS_HD void qs_build_step_tid(const QsPass& P, int s, int e, QsStepTid* tab, uint32_t nthr_log2) {
+// Entry e (0..80) of a step's table: 0..15 -> jA, 16..47 -> jB, 48..63 -> hi,
+// 64..79 -> sdepb, 80 -> the scalar fields.
+#define QS_TAB_ENTRIES 81
+QS_HD void qs_build_step_tab(const QsPass& P, int s, int e, QsStepTab* tab, uint32_t nthr_log2) {
   const QsStep& st = P.steps[s];
   const int nfree = (int)P.T - st.r;
   const int lo_bits = nfree < (int)nthr_log2 ? nfree : (int)nthr_log2;
   if (e < 16) {
     const int c = lo_bits < 4 ? lo_bits : 4;
     tab->jA[e] = (uint16_t)qs_scatter8((uint32_t)e, st.fpos, c);
-  } else {
+  } else if (e < 48) {
     const int c = lo_bits - 4 < 0 ? 0 : (lo_bits - 4 > 5 ? 5 : lo_bits - 4);
     tab->jB[e - 16] = (uint16_t)qs_scatter8((uint32_t)(e - 16), st.fpos + 4, c);
-  }
-}
-
-// Uniform-indexed part (host, at plan time; lives in QsPass::uni).
-inline void qs_build_step_uni(QsPass& P, int s, uint32_t nthr_log2) {
-  const QsStep& st = P.steps[s];
-  QsStepUni* tab = &P.uni[s];
-  const int nfree = (int)P.T - st.r;
-  const int lo_bits = nfree < (int)nthr_log2 ? nfree : (int)nthr_log2;
-  for (int i = 0; i < 16; ++i) {
-    const uint32_t jhi = qs_scatter8((uint32_t)i, st.fpos + nthr_log2, nfree - lo_bits);
-    tab->hi[i] = jhi | (qs_swz(jhi) << 16);
-  }
-  const int r = st.r;
-  for (int m = 0; m < 16; ++m) {
+  } else if (e < 64) {
+    const uint32_t jhi = qs_scatter8((uint32_t)(e - 48), st.fpos + nthr_log2, nfree - lo_bits);
+    tab->hi[e - 48] = jhi | (qs_swz(jhi) << 16);
+  } else if (e < 80) {
     // amplitude m: matrix factor f is bit (r-1-f) of m and sits at local position gpos[f]
+    const int m = e - 64;
     uint32_t d = 0;
-    for (int f = 0; f < r; ++f) d |= (uint32_t)((m >> (r - 1 - f)) & 1) << st.gpos[f];
+    for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
     tab->sdepb[m] = qs_swz(d) << 4;
+  } else {
+    const int r = st.r;
+    uint32_t qg = 0;
+    bool all_rot = st.kind == QS_STEP_1Q;
+    for (int f = 0; f < QS_MAX_R; ++f) {
+      tab->ng[f] = f < r ? st.ng[f] : (uint16_t)0;
+      tab->gpos[f] = f < r ? st.gpos[f] : (uint8_t)0;
+      if (f < r && st.form[f] != QS_FORM_ROT) all_rot = false;
+    }
+    for (int m = 0; m < (1 << r); ++m) {
+      uint32_t q = 0;
+      for (int f = 0; f < r; ++f)
+        if ((m >> (r - 1 - f)) & 1)
+          for (int f2 = f + 1; f2 < r; ++f2)
+            if ((m >> (r - 1 - f2)) & 1) q ^= ((uint32_t)st.ng[f] >> st.gpos[f2]) & 1u;
+      qg |= q << m;
+    }
+    tab->qg = (uint16_t)qg;
+    tab->all_rot = all_rot ? 1 : 0;
   }
-  uint32_t qg = 0;
-  bool all_rot = st.kind == QS_STEP_1Q;
-  for (int f = 0; f < QS_MAX_R; ++f) {
-    tab->ng[f] = f < r ? st.ng[f] : (uint16_t)0;
-    tab->gpos[f] = f < r ? st.gpos[f] : (uint8_t)0;
-    if (f < r && st.form[f] != QS_FORM_ROT) all_rot = false;
-  }
-  for (int m = 0; m < (1 << r); ++m) {
-    uint32_t q = 0;
-    for (int f = 0; f < r; ++f)
-      if ((m >> (r - 1 - f)) & 1)
-        for (int f2 = f + 1; f2 < r; ++f2)
-          if ((m >> (r - 1 - f2)) & 1) q ^= ((uint32_t)st.ng[f] >> st.gpos[f2]) & 1u;
-    qg |= q << m;
-  }
-  tab->qg = (uint16_t)qg;
-  tab->all_rot = all_rot ? 1 : 0;
-  tab->pad = 0;
 }
 
-// Load/store, final-sign and tile-base tables (host, at plan time; QsPass::io).
-inline void qs_build_io(QsPass& P, uint32_t nthr_log2) {
-  QsIoTab* io = &P.io;
+QS_HD void qs_build_io_tab(const QsPass& P, uint32_t i, QsIoTab* io, uint32_t nthr_log2) {
+  const uint32_t jhi = i << nthr_log2;
+  io->gbyte[i] = ((P.T <= nthr_log2) ? 0ull : qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2))) << 4;
+  io->sbyte[i] = qs_swz(jhi & ((1u << P.T) - 1u)) << 4;
+  io->fin_neigh[i] = 0;
+  if (P.fin_has_sign && jhi < (1u << P.T)) io->fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
+}
+QS_HD void qs_build_base_tab(const QsPass& P, uint32_t e, QsIoTab* io) {   // e in [0, 256)
+  io->base_tab[e >> 6][e & 63u] = qs_tile_base(P, (uint64_t)(e & 63u) << (6 * (e >> 6)));
+}
+// fin_q is a bit mask over i; build it with one thread (or sequentially on the host)
+QS_HD uint64_t qs_build_fin_q(const QsPass& P, uint32_t nthr_log2) {
   uint64_t q = 0;
+  if (!P.fin_has_sign) return 0;
   for (uint32_t i = 0; i < QS_MAX_ITER; ++i) {
     const uint32_t jhi = i << nthr_log2;
-    io->gbyte[i] = ((P.T <= nthr_log2) ? 0ull : qs_scatter64(i, P.tile_bits + nthr_log2, (int)(P.T - nthr_log2))) << 4;
-    io->sbyte[i] = qs_swz(jhi & ((1u << P.T) - 1u)) << 4;
-    io->fin_neigh[i] = 0;
-    if (P.fin_has_sign && jhi < (1u << P.T)) {
-      io->fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
-      q |= (uint64_t)qs_fin_quad(P, jhi) << i;
-    }
+    if (jhi < (1u << P.T)) q |= (uint64_t)qs_fin_quad(P, jhi) << i;
   }
-  io->fin_q = q;
-  for (uint32_t e = 0; e < 256; ++e)
-    io->base_tab[e >> 6][e & 63u] = qs_tile_base(P, (uint64_t)(e & 63u) << (6 * (e >> 6)));
+  return q;
 }
 
 // ---- per-tile sign data ---------------------------------------------------------------------
@@ -192,8 +184,7 @@ QS_HD void qs_flip(qs_c128& a, uint32_t sign_bit) {
 // cp.async on the device (so the next tile streams in while this one computes).
 template <class Copy>
 QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, uint64_t base, uint32_t tid,
-                         uint32_t nthr_log2, uint64_t glo, Copy copy) {
-  const QsIoTab& io = P.io;
+                         uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, Copy copy) {
   const uint32_t niter = P.T > nthr_log2 ? 1u << (P.T - nthr_log2) : (tid < (1u << P.T) ? 1u : 0u);
   const uint32_t slob = qs_swz(tid) << 4;
   const char* g0 = reinterpret_cast<const char*>(state) + ((base | glo) << 4);   // disjoint bits: | == +
@@ -204,8 +195,8 @@ QS_HD void qs_phase_load(const QsPass& P, const qs_c128* state, qs_c128* tile, u
 // ---- phase: shared -> global, with the pass's final sign block ---------------
 // fin_qlo = Q(tid) of the final block (tile independent, computed once per launch).
 QS_HD void qs_phase_store(const QsPass& P, qs_c128* state, const qs_c128* tile, uint64_t base, uint32_t tid,
-                          uint32_t nthr_log2, uint64_t glo, uint32_t fin_qlo, uint32_t zmask, uint32_t gsign) {
-  const QsIoTab& io = P.io;
+                          uint32_t nthr_log2, uint64_t glo, const QsIoTab& io, uint32_t fin_qlo,
+                          uint32_t zmask, uint32_t gsign) {
   const uint32_t niter = P.T > nthr_log2 ? 1u << (P.T - nthr_log2) : (tid < (1u << P.T) ? 1u : 0u);
   const uint32_t slob = qs_swz(tid) << 4;
   char* g0 = reinterpret_cast<char*>(state) + ((base | glo) << 4);
@@ -270,9 +261,8 @@ QS_HD void qs_mat2_rot(const double* __restrict__ m, qs_c128& a0, qs_c128& a1) {
 // parity(m & W) + qg(m) with W_f = z_f + parity(j0 & ng[f])   (plan.h).
 template <int R, bool DENSE>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                         uint32_t zg, const QsStepTid& ttab, int debug_skip = 0) {
+                         uint32_t zg, const QsStepTab& tab, int debug_skip = 0) {
   const QsStep& st = P.steps[s];
-  const QsStepUni& tab = P.uni[s];
   const uint32_t nwork = 1u << (P.T - R);
   const uint32_t nthr = 1u << nthr_log2;
   const bool has_sign = st.has_sign != 0;
@@ -287,7 +277,7 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   const uint32_t qg = tab.qg;              // bit m: pairs inside the group
   const bool all_rot = tab.all_rot != 0;
 
-  const uint32_t jlo = (uint32_t)ttab.jA[tid & 15u] | (uint32_t)ttab.jB[(tid >> 4) & 31u];
+  const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
   const uint32_t slo = qs_swz(jlo);
   char* const t0 = reinterpret_cast<char*>(tile);
 
@@ -416,7 +406,7 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 // of the calling kernel); DENSE says whether dense (k >= 2) steps may occur.
 template <int MAXR, bool DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
-                             uint32_t zmask, const QsStepTid& tab, int debug_skip = 0) {
+                             uint32_t zmask, const QsStepTab& tab, int debug_skip = 0) {
   const int r = P.steps[s].r;
   if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
   else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zmask, tab, debug_skip);
