@@ -27,7 +27,6 @@ struct DevCtx {
   double* d_partials = nullptr;   // [kReduceBlocks][2]
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
-  unsigned* d_sm_arrival = nullptr;  // [256] CTA arrival counters per SM (never reset: used mod occupancy)
   int occ[4] = {0, 0, 0, 0};      // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
@@ -63,8 +62,6 @@ int bind_device(const void* ptr, DevCtx** ctx) {
     QS_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks));
     QS_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 2));
     QS_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 2));
-    QS_CUDA(cudaMalloc(&c.d_sm_arrival, sizeof(unsigned) * 256));
-    QS_CUDA(cudaMemset(c.d_sm_arrival, 0, sizeof(unsigned) * 256));
     c.ready = true;
   }
   *ctx = &c;
@@ -92,8 +89,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int MAXR, bool DENSE>
 __global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1)
                                                : QS_THREADS_LOG2 <= 7 ? 3 : (MAXR <= 3 ? 3 : 2)))
-k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf,
-            unsigned* sm_arrival, int stagger_cycles, int occ, int debug_skip) {
+k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf, int debug_skip) {
   extern __shared__ __align__(16) unsigned char qs_smem[];
   qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
   qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
@@ -113,22 +109,6 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
   const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
   const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
   __syncthreads();
-
-  // The CTAs that share an SM all run the same load / compute / store cycle; started
-  // together they stay in lockstep (all loading, then all computing) and HBM and the
-  // FP64 pipe take turns idling.  Offset them by a fraction of the cycle instead.
-  if (stagger_cycles > 0) {
-    __shared__ unsigned s_rank;
-    if (tid == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_rank = atomicAdd(&sm_arrival[smid & 255u], 1u) % (unsigned)occ;
-    }
-    __syncthreads();
-    const long long wait = (long long)s_rank * stagger_cycles;
-    const long long t0 = clock64();
-    while (clock64() - t0 < wait) __nanosleep(200);
-  }
 
   uint64_t t = blockIdx.x;
   if (dbuf && t < ntiles)
@@ -170,7 +150,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, i
   cp_async_wait<0>();
 }
 
-typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, unsigned*, int, int, int);
+typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, int);
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
@@ -203,25 +183,6 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
   uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
   if (grid > ntiles) grid = ntiles;
-  // stagger the co-resident CTAs by 1/occ of the estimated per-tile time
-  // (memory at ~18 B/clk/SM, FP64 at 64 FMA/clk/SM); QSIM_STAGGER=0 disables
-  static const int stagger_env = [] {
-    const char* e = getenv("QSIM_STAGGER");
-    return e ? atoi(e) : -1;
-  }();
-  int stagger = 0;
-  if (occ > 1 && ntiles >= grid * 4 && stagger_env != 0) {
-    double dp_per_amp = 0.0;
-    for (uint32_t s = 0; s < P.nsteps; ++s) {
-      const QsStep& st = P.steps[s];
-      if (st.kind == QS_STEP_DENSE) dp_per_amp += 4.0 * (1 << st.r);
-      else
-        for (int f = 0; f < st.r; ++f) dp_per_amp += st.form[f] == QS_FORM_GENERAL ? 8.0 : 4.0;
-    }
-    const double amps = (double)(1u << P.T);
-    const double cycles = amps * 32.0 / 18.0 + amps * dp_per_amp / 64.0;
-    stagger = stagger_env > 0 ? stagger_env : (int)(cycles / occ);
-  }
   // QSIM_DEBUG_SKIP (development only): bit 0 skips the global loads, bit 1 the global
   // stores of a pass, bit 2 the matrix arithmetic, to time the parts on their own
   // (results are garbage)
@@ -229,8 +190,7 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
     const char* e = getenv("QSIM_DEBUG_SKIP");
     return e ? atoi(e) : 0;
   }();
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, ctx->d_sm_arrival, stagger, occ,
-                                                          debug_skip);
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, debug_skip);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;
