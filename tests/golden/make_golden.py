@@ -325,6 +325,41 @@ def gen_sim_measure():
     save("sim_measure.npz", {"circuit": specs, "runs": meta}, arrays)
 
 
+
+
+def gen_layering():
+    """MB layer scheduling (GKP/transpiler.py:65-209) of random circuits: depth, gate
+    count and the filled layer contents, for quantum_computations_b200.layering."""
+    from simulators.dv_simulator.simulator import ClassicalControl as RCC
+    from simulators.gkp_simulator.transpiler import MBGKPCircuit
+    rng = np.random.default_rng(77)
+    cases = []
+    names1 = ["I", "H", "P", "Pdg", "T", "Tdg", "X", "Y", "Z"]
+    for _ in range(30):
+        n = int(rng.integers(2, 6))
+        length = int(rng.integers(3, 25))
+        circ = []
+        for _ in range(length):
+            if rng.random() < 0.3:
+                i = int(rng.integers(0, n - 1))
+                cls = rg.CZ if rng.random() < 0.6 else rg.SWAP
+                circ.append(cls(i, i + 1) if rng.random() < 0.5 else cls(i + 1, i))
+            else:
+                circ.append(getattr(rg, names1[int(rng.integers(0, len(names1)))])(int(rng.integers(0, n))))
+        mb = MBGKPCircuit.transpile(circ, n)
+        d0, c0 = mb.depth(), mb.count()
+        mb.fill()
+        desc = []
+        for layer in mb._layers:
+            names = [(repr(g.gate) + "?") if isinstance(g, RCC) else repr(g) for g in layer.gates]
+            desc.append({"gates": names, "paulis": [list(p) for p in layer.paulis]})
+        cases.append({"n": n, "circuit": [to_spec(g, {}) for g in circ], "depth": d0, "count": c0,
+                      "count_filled": mb.count(), "layers": desc})
+    with open(os.path.join(HERE, "layering.json"), "w") as f:
+        json.dump(cases, f)
+    print(f"wrote layering.json: {len(cases)} cases")
+
+
 if __name__ == "__main__":
     fast = "--fast" in sys.argv
     gen_single_gates()
@@ -338,3 +373,4 @@ if __name__ == "__main__":
     gen_metrics()
     gen_sim_measure()
     gen_circuits(fast)
+    gen_layering()
