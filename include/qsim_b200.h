@@ -122,11 +122,11 @@ int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void* st
 /* ---- batched tiny-circuit executor (replaces the sample loop of
  *      PAPER/randomised_benchmarking.py:65-75) --------------------------------------
  * B independent registers of nq <= 2 qubits kept as density matrices (dim = 2^nq).
- * Sequence b applies opcodes[offsets[b] .. offsets[b+1]); opcode o multiplies
+ * Sequence b applies opcodes[offsets[b] .. offsets[b+1]) (16-bit codes); opcode o multiplies
  * vec(rho) by superops[o] (dim^2 x dim^2) and the ideal ket by unitaries[o]
  * (dim x dim).  Outputs per sequence: fidelity <psi|rho|psi> and purity tr rho^2.
  * All pointers are DEVICE pointers except the scalar arguments. */
-int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets,
+int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t* offsets,
                   int n_opcodes, const double* superops, const double* unitaries,
                   const double* rho0, const double* psi0, double* out_fidelity, double* out_purity,
                   double* out_rho, void* stream);

@@ -63,19 +63,19 @@ class BatchedSimulator:
                     acc += np.kron(kf, np.conjugate(kf))
                 sup = acc @ sup
         code = len(self._superops)
-        if code >= 256:
-            raise NotImplementedError("more than 256 distinct gates in one batch")
+        if code >= 65536:
+            raise NotImplementedError("more than 65536 distinct gates in one batch")
         self._codes[key] = code
         self._superops.append(np.ascontiguousarray(sup))
         self._unitaries.append(np.ascontiguousarray(u))
         return code
 
     def encode(self, circuits):
-        """(opcodes uint8, offsets int64) for a list of circuits."""
+        """(opcodes uint16, offsets int64) for a list of circuits."""
         lengths = np.fromiter((len(c) for c in circuits), dtype=np.int64, count=len(circuits))
         offsets = np.zeros(len(circuits) + 1, dtype=np.int64)
         np.cumsum(lengths, out=offsets[1:])
-        codes = np.empty(int(offsets[-1]), dtype=np.uint8)
+        codes = np.empty(int(offsets[-1]), dtype=np.uint16)
         pos = 0
         opcode = self._opcode
         for circ in circuits:
@@ -107,7 +107,7 @@ class BatchedSimulator:
         if B == 0:
             return {"fidelity": np.zeros(0), "purity": np.zeros(0)}
         if len(codes) == 0:
-            codes = np.zeros(1, dtype=np.uint8)            # keep the device pointer valid
+            codes = np.zeros(1, dtype=np.uint16)           # keep the device pointer valid
         sup = np.stack(self._superops) if self._superops else np.zeros((1, d * d, d * d), np.complex128)
         uni = np.stack(self._unitaries) if self._unitaries else np.zeros((1, d, d), np.complex128)
 

@@ -74,7 +74,7 @@ QS_HD qs_c128 qs_generic_amp(const qs_c128* in, const double* mat, const int* bi
 // times a dim^2 x dim^2 superoperator per opcode, ideal ket times a dim x dim
 // unitary per opcode; then fidelity <psi|rho|psi> and purity tr(rho rho).
 template <int DIM>
-QS_HD void qs_rb_sequence(const uint8_t* codes, int64_t len, const double* superops,
+QS_HD void qs_rb_sequence(const uint16_t* codes, int64_t len, const double* superops,
                           const double* unitaries, const double* rho0, const double* psi0,
                           double* out_fid, double* out_pur, double* out_rho) {
   constexpr int D2 = DIM * DIM;

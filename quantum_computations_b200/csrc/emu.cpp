@@ -332,13 +332,13 @@ int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void*) {
   return QSIM_OK;
 }
 
-int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets, int n_opcodes,
+int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t* offsets, int n_opcodes,
                   const double* superops, const double* unitaries, const double* rho0, const double* psi0,
                   double* out_fidelity, double* out_purity, double* out_rho, void*) {
   if (!opcodes || !offsets || !superops || !unitaries || !rho0 || !psi0 || !out_fidelity || !out_purity)
     return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: null argument");
   if (nq < 1 || nq > 2) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_rb_batch: nq must be 1 or 2");
-  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 256) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
+  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 65536) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
   for (int64_t b = 0; b < n_seq; ++b) {
     const int64_t lo = offsets[b], hi = offsets[b + 1];
     if (nq == 2)

@@ -373,7 +373,7 @@ int reduce_to_host(DevCtx* ctx, F f, uint64_t count, double* out2, cudaStream_t 
 // Batched tiny-circuit executor
 // =====================================================================================
 template <int DIM>
-__global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint8_t* __restrict__ codes,
+__global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint16_t* __restrict__ codes,
                                                   const int64_t* __restrict__ offsets,
                                                   const double* __restrict__ superops,
                                                   const double* __restrict__ unitaries,
@@ -644,13 +644,13 @@ int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void* st
   return reduce_to_host(ctx, f, 1ull << n_qubits, out_re_im, (cudaStream_t)stream);
 }
 
-int qsim_rb_batch(int nq, int64_t n_seq, const uint8_t* opcodes, const int64_t* offsets, int n_opcodes,
+int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t* offsets, int n_opcodes,
                   const double* superops, const double* unitaries, const double* rho0, const double* psi0,
                   double* out_fidelity, double* out_purity, double* out_rho, void* stream) {
   if (!opcodes || !offsets || !superops || !unitaries || !rho0 || !psi0 || !out_fidelity || !out_purity)
     return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: null argument");
   if (nq < 1 || nq > 2) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_rb_batch: nq must be 1 or 2");
-  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 256) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
+  if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 65536) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
   if (n_seq == 0) return QSIM_OK;
   DevCtx* ctx = nullptr;
   int rc = bind_device(out_fidelity, &ctx);
