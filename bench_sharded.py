@@ -46,7 +46,7 @@ def run_sharded(args, world, rank, local_rank):
     zero = [State.ZERO.get()] * n
 
     def step():
-        state.set_product(zero)
+        sim.prepare(zero)
         sim.run()
 
     for _ in range(args.warmup):

@@ -131,18 +131,21 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
                   const double* rho0, const double* psi0, double* out_fidelity, double* out_purity,
                   double* out_rho, void* stream);
 
-/* ---- global<->local qubit swap helpers for sharded states -------------------------
- * A state of n qubits sharded over 2^g ranks keeps reference qubits 0..g-1 in the
- * rank number.  Exchanging global qubit qg with local qubit ql moves, on every rank,
- * the half of the shard whose ql-bit differs from the rank's qg-bit.  These two
- * kernels gather that half into a contiguous send buffer and scatter the received
- * half back; the transfer itself is the caller's (NCCL send/recv or P2P copy).
- * first/count select a chunk of the 2^(n_local-1) travelling amplitudes (for pipelining);
- * the buffer holds `count` amplitudes. */
-int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit,
-                   uint64_t first, uint64_t count, void* stream);
-int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit,
-                     uint64_t first, uint64_t count, void* stream);
+/* ---- global<->local qubit exchange helpers for sharded states ----------------------
+ * A state of n qubits sharded over 2^g ranks keeps g qubits in the rank number.
+ * Exchanging k rank qubits with k local qubits at once is an all-to-all among the 2^k
+ * ranks that differ in those rank bits: rank R sends to partner R^d the 2^(n_local-k)
+ * amplitudes whose k local bits spell the PARTNER's rank bits, and receives into the
+ * same positions (k = 1 is the plain global<->local swap of half a shard).  These two
+ * kernels gather such a block into a contiguous send buffer and scatter a received
+ * block back; the transfer itself is the caller's (P2P copy or NCCL/gloo send/recv).
+ * local_qubits[i] (reference-style numbering inside the shard) is fixed to
+ * bit_values[i]; first/count select a chunk of the block (for pipelining); the buffer
+ * holds `count` amplitudes.  nbits <= 8. */
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int nbits, const int* local_qubits,
+                   const int* bit_values, uint64_t first, uint64_t count, void* stream);
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, const int* local_qubits,
+                     const int* bit_values, uint64_t first, uint64_t count, void* stream);
 
 /* ---- peer-to-peer staging for the swaps (one process per GPU) -----------------------
  * The travelling half shard moves with the copy engines, not with SM kernels: every

@@ -16,6 +16,14 @@ QS_HD uint64_t qs_insert_bit(uint64_t r, int pos, uint64_t bit) {
   return ((r >> pos) << (pos + 1)) | (bit << pos) | low;
 }
 
+// Index of travelling amplitude r of a k-bit exchange: the k bits at positions pos[]
+// (ascending) are fixed to val[], the other bits are r's, in order.
+struct QsBitSel { int k; int pos[8]; int val[8]; };
+QS_HD uint64_t qs_deposit(uint64_t r, const QsBitSel& sel) {
+  for (int i = 0; i < sel.k; ++i) r = qs_insert_bit(r, sel.pos[i], (uint64_t)sel.val[i]);
+  return r;
+}
+
 // parse_state for list[State] (DV/simulator.py:26): amplitude i of the product
 // of n single-qubit kets; amps = n x 2 complex, qubit q first.
 QS_HD qs_c128 qs_product_amp(const double* amps, int n, uint64_t i) {

@@ -10,6 +10,8 @@
 // and raises when that library or a CUDA device is missing.
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "elem_ops.h"
@@ -352,30 +354,51 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
   return QSIM_OK;
 }
 
-int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
-                   uint64_t count, void*) {
+static int swap_select(const char* who, int n_local, int nbits, const int* local_qubits, const int* bit_values,
+                       uint64_t first, uint64_t count, QsBitSel* sel) {
+  if (n_local < 1 || nbits < 1 || nbits > 8 || nbits > n_local || !local_qubits || !bit_values)
+    return qs::fail(QSIM_ERR_ARG, std::string(who) + ": bad bit list");
+  sel->k = nbits;
+  for (int i = 0; i < nbits; ++i) {
+    if (local_qubits[i] < 0 || local_qubits[i] >= n_local || (bit_values[i] | 1) != 1)
+      return qs::fail(QSIM_ERR_ARG, std::string(who) + ": bad qubit or bit");
+    sel->pos[i] = n_local - 1 - local_qubits[i];
+    sel->val[i] = bit_values[i];
+  }
+  for (int i = 1; i < nbits; ++i)
+    for (int j = i; j > 0 && sel->pos[j] < sel->pos[j - 1]; --j) {
+      std::swap(sel->pos[j], sel->pos[j - 1]);
+      std::swap(sel->val[j], sel->val[j - 1]);
+    }
+  for (int i = 1; i < nbits; ++i)
+    if (sel->pos[i] == sel->pos[i - 1]) return qs::fail(QSIM_ERR_ARG, std::string(who) + ": repeated qubit");
+  if (first + count > (1ull << (n_local - nbits)))
+    return qs::fail(QSIM_ERR_ARG, std::string(who) + ": chunk out of range");
+  return QSIM_OK;
+}
+
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int nbits, const int* local_qubits,
+                   const int* bit_values, uint64_t first, uint64_t count, void*) {
   if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
-  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
-    return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
-  const int pos = n_local - 1 - local_qubit;
+  QsBitSel sel;
+  const int rc = swap_select("qsim_swap_pack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
+  if (rc != QSIM_OK) return rc;
   const qs_c128* s = (const qs_c128*)shard;
   qs_c128* b = (qs_c128*)sendbuf;
-  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: chunk out of range");
-  for (uint64_t r = 0; r < count; ++r) b[r] = s[qs_insert_bit(first + r, pos, (uint64_t)(1 - keep_bit))];
+  for (uint64_t r = 0; r < count; ++r) b[r] = s[qs_deposit(first + r, sel)];
   ++g_launches;
   return QSIM_OK;
 }
 
-int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
-                     uint64_t count, void*) {
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, const int* local_qubits,
+                     const int* bit_values, uint64_t first, uint64_t count, void*) {
   if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
-  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
-    return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
-  const int pos = n_local - 1 - local_qubit;
+  QsBitSel sel;
+  const int rc = swap_select("qsim_swap_unpack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
+  if (rc != QSIM_OK) return rc;
   qs_c128* s = (qs_c128*)shard;
   const qs_c128* b = (const qs_c128*)recvbuf;
-  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: chunk out of range");
-  for (uint64_t r = 0; r < count; ++r) s[qs_insert_bit(first + r, pos, (uint64_t)(1 - keep_bit))] = b[r];
+  for (uint64_t r = 0; r < count; ++r) s[qs_deposit(first + r, sel)] = b[r];
   ++g_launches;
   return QSIM_OK;
 }

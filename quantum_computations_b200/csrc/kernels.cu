@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "elem_ops.h"
@@ -233,18 +234,18 @@ __global__ void k_generic(const qs_c128* __restrict__ in, qs_c128* __restrict__ 
     out[i] = qs_generic_amp(in, mat, bl.bits, k, i);
 }
 
-__global__ void k_swap_pack(const qs_c128* __restrict__ shard, qs_c128* __restrict__ buf, int pos,
-                            uint64_t bit, uint64_t first, uint64_t count) {
+__global__ void k_swap_pack(const qs_c128* __restrict__ shard, qs_c128* __restrict__ buf, QsBitSel sel,
+                            uint64_t first, uint64_t count) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
        r += (uint64_t)gridDim.x * blockDim.x)
-    buf[r] = shard[qs_insert_bit(first + r, pos, bit)];
+    buf[r] = shard[qs_deposit(first + r, sel)];
 }
 
-__global__ void k_swap_unpack(qs_c128* __restrict__ shard, const qs_c128* __restrict__ buf, int pos,
-                              uint64_t bit, uint64_t first, uint64_t count) {
+__global__ void k_swap_unpack(qs_c128* __restrict__ shard, const qs_c128* __restrict__ buf, QsBitSel sel,
+                              uint64_t first, uint64_t count) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
        r += (uint64_t)gridDim.x * blockDim.x)
-    shard[qs_insert_bit(first + r, pos, bit)] = buf[r];
+    shard[qs_deposit(first + r, sel)] = buf[r];
 }
 
 unsigned stream_grid(const DevCtx* ctx, uint64_t count, int threads) {
@@ -668,35 +669,59 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
   return QSIM_OK;
 }
 
-int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
-                   uint64_t count, void* stream) {
+// fills `sel` (positions ascending) from reference-style local qubit numbers
+static int swap_select(const char* who, int n_local, int nbits, const int* local_qubits, const int* bit_values,
+                       uint64_t first, uint64_t count, QsBitSel* sel) {
+  if (n_local < 1 || nbits < 1 || nbits > 8 || nbits > n_local || !local_qubits || !bit_values)
+    return qs::fail(QSIM_ERR_ARG, std::string(who) + ": bad bit list");
+  sel->k = nbits;
+  for (int i = 0; i < nbits; ++i) {
+    if (local_qubits[i] < 0 || local_qubits[i] >= n_local || (bit_values[i] | 1) != 1)
+      return qs::fail(QSIM_ERR_ARG, std::string(who) + ": bad qubit or bit");
+    sel->pos[i] = n_local - 1 - local_qubits[i];
+    sel->val[i] = bit_values[i];
+  }
+  for (int i = 1; i < nbits; ++i)                 // insertion sort by position
+    for (int j = i; j > 0 && sel->pos[j] < sel->pos[j - 1]; --j) {
+      std::swap(sel->pos[j], sel->pos[j - 1]);
+      std::swap(sel->val[j], sel->val[j - 1]);
+    }
+  for (int i = 1; i < nbits; ++i)
+    if (sel->pos[i] == sel->pos[i - 1]) return qs::fail(QSIM_ERR_ARG, std::string(who) + ": repeated qubit");
+  if (first + count > (1ull << (n_local - nbits)))
+    return qs::fail(QSIM_ERR_ARG, std::string(who) + ": chunk out of range");
+  return QSIM_OK;
+}
+
+int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int nbits, const int* local_qubits,
+                   const int* bit_values, uint64_t first, uint64_t count, void* stream) {
   if (!shard || !sendbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: null argument");
-  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
-    return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: bad qubit or bit");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(shard, &ctx);
+  QsBitSel sel;
+  int rc = swap_select("qsim_swap_pack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
   if (rc != QSIM_OK) return rc;
-  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_pack: chunk out of range");
+  DevCtx* ctx = nullptr;
+  rc = bind_device(shard, &ctx);
+  if (rc != QSIM_OK) return rc;
   if (count == 0) return QSIM_OK;
   k_swap_pack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const qs_c128*)shard, (qs_c128*)sendbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), first, count);
+      (const qs_c128*)shard, (qs_c128*)sendbuf, sel, first, count);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;
 }
 
-int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int local_qubit, int keep_bit, uint64_t first,
-                     uint64_t count, void* stream) {
+int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, const int* local_qubits,
+                     const int* bit_values, uint64_t first, uint64_t count, void* stream) {
   if (!shard || !recvbuf) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: null argument");
-  if (n_local < 1 || local_qubit < 0 || local_qubit >= n_local || (keep_bit | 1) != 1)
-    return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: bad qubit or bit");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(shard, &ctx);
+  QsBitSel sel;
+  int rc = swap_select("qsim_swap_unpack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
   if (rc != QSIM_OK) return rc;
-  if (first + count > (1ull << (n_local - 1))) return qs::fail(QSIM_ERR_ARG, "qsim_swap_unpack: chunk out of range");
+  DevCtx* ctx = nullptr;
+  rc = bind_device(shard, &ctx);
+  if (rc != QSIM_OK) return rc;
   if (count == 0) return QSIM_OK;
   k_swap_unpack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
-      (qs_c128*)shard, (const qs_c128*)recvbuf, n_local - 1 - local_qubit, (uint64_t)(1 - keep_bit), first, count);
+      (qs_c128*)shard, (const qs_c128*)recvbuf, sel, first, count);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

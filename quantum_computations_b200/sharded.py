@@ -1,30 +1,33 @@
-"""State vectors larger than one GPU: shard by the top qubits, swap on demand.
+"""State vectors larger than one GPU: shard by g qubits, exchange them in stages.
 
 The reference has no distributed path at all; this module
 is what ``BASELINE.json`` configuration C5 (34 qubits over 8 B200s) needs.
 
 Layout.  A register of ``n`` qubits over ``P = 2^g`` ranks: rank ``r`` holds the
-``2^(n-g)`` amplitudes whose top ``g`` index bits equal ``r``.  The *physical*
-index bits ``0 .. n-g-1`` are local, bits ``n-g .. n-1`` are the rank number.
-A table maps every logical index bit (reference qubit ``q`` is logical bit
-``n-1-q``) to the physical bit it currently occupies.
+``2^(n-g)`` amplitudes whose top ``g`` *physical* index bits equal ``r``.  Physical
+bits ``0 .. n-g-1`` are local, bits ``n-g .. n-1`` are the rank number.  A table maps
+every logical index bit (reference qubit ``q`` is logical bit ``n-1-q``) to the
+physical bit it currently occupies, and every rank bit carries a *flip* flag: with
+the flag set, rank bit value ``b`` stands for logical value ``1-b``.
 
-Execution.  Gates are consumed in program order:
+Execution.  The circuit is cut into *stages*; inside a stage the set of rank qubits
+is fixed and everything runs on the shard through the single-GPU fused planner:
 
-* a gate whose non-diagonal action touches only local bits joins the current
-  local segment, which is run by the single-GPU fused planner on the shard;
-* diagonal gates (Z, RZ, P, T, CZ, ...) never need communication: for the bits
-  that live in the rank number the diagonal is restricted to this rank's values
-  and becomes a smaller diagonal gate (or a scalar) on the shard;
-* a non-diagonal gate on a rank bit triggers a *global<->local swap*: that bit
-  changes places with the local bit whose next non-diagonal use lies farthest in
-  the future.  Every rank keeps the half of its shard that already agrees with
-  its rank bit and exchanges the other half with the partner rank
-  ``r ^ 2^(bit)`` -- one send and one receive of half a shard per rank, all
-  ``P/2`` pairs at once over NVLink/NVSwitch (``torch.distributed`` P2P on
-  NCCL).  When the local bit is the top local bit the halves are contiguous and
-  travel without staging; otherwise ``qsim_swap_pack`` / ``qsim_swap_unpack``
-  gather and scatter them.
+* diagonal gates (Z, RZ, P, T, CZ, ...) never need communication: for the bits that
+  live in the rank number the diagonal is restricted to this rank's values and
+  becomes a smaller diagonal gate (or a scalar) on the shard;
+* an antidiagonal single-qubit gate (X, Y, ...) on a rank qubit only relabels the
+  ranks: the shard is scaled by one matrix entry and the flip flag toggles;
+* any other gate on a rank qubit blocks, and so does whatever depends on it.  When
+  nothing more can run, the next stage's rank qubits are chosen -- the ``g`` qubits
+  whose next blocking gate lies farthest ahead -- and all of them trade places with
+  local qubits in ONE all-to-all exchange: with ``k`` qubits moving, every rank keeps
+  ``1/2^k`` of its shard and sends ``1/2^k`` to each of the ``2^k - 1`` ranks that
+  differ in those rank bits (0.875 of a shard for k = 3, where three single swaps
+  would move 1.5).  ``qsim_swap_pack`` / ``qsim_swap_unpack`` gather and scatter the
+  travelling blocks; the transfer is a copy-engine push over NVLink (CUDA IPC) on
+  GPUs and a send/recv elsewhere.  The first stage costs nothing: the initial product
+  state is built directly in the layout the schedule wants.
 """
 from __future__ import annotations
 
@@ -86,6 +89,7 @@ class ShardedState:
         self.n_local = self.n - self.g
         self.backend = backend or engine.get_backend()
         self.phys = list(range(self.n))           # phys[logical bit] = physical bit
+        self.flip = [0] * self.g                  # flip[i]: rank bit i holds the complemented logical value
         self.buf = self.backend.empty(1 << self.n_local)
         self.swaps = 0
         self.swap_seconds = 0.0
@@ -94,17 +98,26 @@ class ShardedState:
         self._as_torch = as_torch or (lambda b: b)
 
     # -- initial states ---------------------------------------------------------------------
-    def set_product(self, vectors) -> None:
-        """|psi> = kron of single-qubit kets (qubit 0 first).  The rank bits select
-        one amplitude of each of the first g kets: a scalar on this rank."""
+    def rank_value(self, phys_bit: int) -> int:
+        """Logical value this rank holds for the qubit living in rank bit ``phys_bit``."""
+        i = phys_bit - self.n_local
+        return ((self.comm.rank >> i) & 1) ^ self.flip[i]
+
+    def set_product(self, vectors, phys=None) -> None:
+        """|psi> = kron of single-qubit kets (qubit 0 first), laid out as ``phys``
+        (default: identity).  The rank bits select one amplitude of each rank qubit's
+        ket: a scalar on this rank."""
         vecs = [np.asarray(v, dtype=np.complex128) for v in vectors]
         assert len(vecs) == self.n
-        self.phys = list(range(self.n))
+        self.phys = list(phys) if phys is not None else list(range(self.n))
+        assert sorted(self.phys) == list(range(self.n))
+        self.flip = [0] * self.g
+        where = {p: l for l, p in enumerate(self.phys)}            # physical bit -> logical bit
         scale = 1.0 + 0.0j
-        for q in range(self.g):                    # reference qubit q = logical bit n-1-q = rank bit
-            bit = (self.comm.rank >> (self.g - 1 - q)) & 1
-            scale *= vecs[q][bit]
-        local = [v.copy() for v in vecs[self.g:]]
+        for p in range(self.n_local, self.n):
+            scale *= vecs[self.n - 1 - where[p]][self.rank_value(p)]
+        # local reference-style qubit j of the shard is physical bit n_local-1-j
+        local = [vecs[self.n - 1 - where[self.n_local - 1 - j]].copy() for j in range(self.n_local)]
         local[0] = local[0] * scale
         amps = np.ascontiguousarray(np.stack(local))
         be = self.backend
@@ -167,93 +180,112 @@ class ShardedState:
         return peer
 
     def swap(self, global_phys: int, local_phys: int) -> None:
-        """Exchange physical rank bit ``global_phys`` with physical local bit ``local_phys``.
+        """Exchange one rank bit with one local bit (half a shard travels)."""
+        self.exchange([(global_phys, local_phys)])
 
-        The travelling half shard is cut into chunks that flow through a three-stage
-        pipeline on three streams: gather (``qsim_swap_pack``) into a staging chunk,
-        transfer, scatter (``qsim_swap_unpack``).  On GPUs the transfer is a copy-engine
-        PULL of the partner's staging chunk over NVLink (CUDA IPC + ``qsim_peer_copy``),
-        ordered between the two processes by a stream-ordered NCCL token exchange, so
-        no SM is spent on communication; elsewhere (gloo tests) it is a send/recv."""
+    def exchange(self, pairs) -> None:
+        """Exchange the physical rank bits with the physical local bits of ``pairs``
+        (``[(global_phys, local_phys), ...]``), all at once.
+
+        With k pairs the 2^k ranks that differ in those rank bits form a group; in round
+        d = 1 .. 2^k-1 every rank trades one block of 2^(n_local-k) amplitudes with the
+        partner whose rank bits differ by the pattern d: it sends the block whose k local
+        bits spell the partner's rank bits and receives into the same positions.  Blocks
+        are cut into chunks that flow through a three-stage pipeline on three streams:
+        gather (``qsim_swap_pack``) into a staging chunk, transfer, scatter
+        (``qsim_swap_unpack``).  On GPUs the transfer is a copy-engine PUSH into the
+        partner's staging chunk over NVLink (CUDA IPC + ``qsim_peer_copy``), fenced on both
+        sides by tiny stream-ordered NCCL token exchanges with that partner, so no SM is
+        spent on communication; elsewhere (gloo tests) it is a send/recv.  Flip flags are
+        the caller's business: the bits move as stored."""
         import time
         be, lib = self.backend, self.backend.lib
-        gi = global_phys - self.n_local            # bit of the rank number
-        keep = (self.comm.rank >> gi) & 1
-        partner = self.comm.rank ^ (1 << gi)
-        half = 1 << (self.n_local - 1)
-        qubit = self.n_local - 1 - local_phys      # local reference-style qubit number
-        chunk = min(half, 1 << self.CHUNK_LOG2)
-        nchunks = half // chunk
+        k = len(pairs)
+        if k == 0:
+            return
+        gis = [gp - self.n_local for gp, _lp in pairs]                 # bits of the rank number
+        if len(set(gis)) != k or len({lp for _gp, lp in pairs}) != k or \
+                any(not 0 <= gi < self.g for gi in gis) or any(not 0 <= lp < self.n_local for _gp, lp in pairs):
+            raise ValueError("exchange: bad bit pairs")
+        qubits = (C.c_int * k)(*[self.n_local - 1 - lp for _gp, lp in pairs])   # local reference-style numbers
+        mine = [(self.comm.rank >> gi) & 1 for gi in gis]
+        block = 1 << (self.n_local - k)
+        chunk = min(block, 1 << self.CHUNK_LOG2)
+        per_block = block // chunk
+        items = []                                   # (partner, bit values of the travelling block, first)
+        for d in range(1, 1 << k):
+            partner = self.comm.rank
+            vals = []
+            for i in range(k):
+                di = (d >> i) & 1
+                partner ^= di << gis[i]
+                vals.append(mine[i] ^ di)
+            for c in range(per_block):
+                items.append((partner, (C.c_int * k)(*vals), c * chunk))
         peer = self._peer_setup(chunk)
         ipc = peer["ipc"]
-        be.synchronize()                           # so the timer below sees the swap alone
+        be.synchronize()                           # so the timer below sees the exchange alone
         t0 = time.perf_counter()
         if ipc:
             send_ptr, recv_ptr = peer["send_ptr"], peer["recv_ptr"]
-            remote = peer["remote_recv"][partner]
         else:
             send_ptr = [be.ptr(b) for b in peer["send"]]
             recv_ptr = [be.ptr(b) for b in peer["recv"]]
         pipe = be.pipeline(3)                      # stream contexts + events (no-ops on the host emulator)
-        packed, ordered, moved, unpacked = {}, {}, {}, {}
+        packed, moved, unpacked = {}, {}, {}
 
-        def token():                               # both ranks have reached this point of their comm streams
+        def token(partner):                        # both ranks have reached this point of their comm streams
             self.comm.exchange(peer["token_out"], peer["token_in"], partner)
 
         def pack(c):
+            _partner, vals, first = items[c]
             with pipe.stage(0):
                 if c >= 2:
-                    pipe.wait(moved[c - 2])        # send[c%2] has left (our own push / send of chunk c-2)
+                    pipe.wait(moved[c - 2])        # send[c%2] has left (our own push / send of item c-2)
                 _capi.check(lib, lib.qsim_swap_pack(be.ptr(self.buf), C.c_void_p(send_ptr[c % 2]), self.n_local,
-                                                    qubit, keep, C.c_uint64(c * chunk), C.c_uint64(chunk),
+                                                    k, qubits, vals, C.c_uint64(first), C.c_uint64(chunk),
                                                     be.stream()))
                 packed[c] = pipe.record()
 
         def unpack(c):
+            _partner, vals, first = items[c]
             with pipe.stage(2):
-                # IPC: the partner's push of chunk c precedes its token c+1 on its comm stream
-                pipe.wait(ordered[c + 1] if ipc else moved[c])
+                pipe.wait(moved[c])
                 _capi.check(lib, lib.qsim_swap_unpack(be.ptr(self.buf), C.c_void_p(recv_ptr[c % 2]), self.n_local,
-                                                      qubit, keep, C.c_uint64(c * chunk), C.c_uint64(chunk),
+                                                      k, qubits, vals, C.c_uint64(first), C.c_uint64(chunk),
                                                       be.stream()))
                 unpacked[c] = pipe.record()
 
-        for c in range(nchunks):
+        for c, (partner, _vals, _first) in enumerate(items):
             pack(c)
             with pipe.stage(1):
                 pipe.wait(packed[c])
                 if c >= 2:
                     pipe.wait(unpacked[c - 2])     # our recv[c%2] is free again
                 if ipc:
-                    # token c: both chunks c are packed and both recv[c%2] are free -> PUSH ours
+                    # first token: both items c are packed and both recv[c%2] are free -> PUSH ours
                     # into the partner's staging with the copy engine (writes are the fast
-                    # direction of NVLink P2P)
-                    token()
-                    ordered[c] = pipe.record()
-                    _capi.check(lib, lib.qsim_peer_copy(C.c_void_p(remote[c % 2]), C.c_void_p(send_ptr[c % 2]),
+                    # direction of NVLink P2P); second token: both pushes have landed
+                    token(partner)
+                    _capi.check(lib, lib.qsim_peer_copy(C.c_void_p(peer["remote_recv"][partner][c % 2]),
+                                                        C.c_void_p(send_ptr[c % 2]),
                                                         C.c_uint64(16 * chunk), be.stream()))
+                    token(partner)
                     self.comm.bytes_exchanged += 16 * chunk
                 else:
                     self.comm.exchange(self._as_torch(peer["send"][c % 2]), self._as_torch(peer["recv"][c % 2]),
                                        partner)
                 moved[c] = pipe.record()
-            if ipc:
-                if c >= 1:
-                    unpack(c - 1)
-            else:
-                unpack(c)
-        if ipc:
-            with pipe.stage(1):
-                token()                            # every push has landed on both sides
-                ordered[nchunks] = pipe.record()
-            unpack(nchunks - 1)
+            unpack(c)
         pipe.join()
         be.synchronize()
         self.swap_seconds += time.perf_counter() - t0
         self.swaps += 1
-        # the two logical bits trade places
-        la, lb = self.phys.index(global_phys), self.phys.index(local_phys)
-        self.phys[la], self.phys[lb] = local_phys, global_phys
+        self.amps_sent = getattr(self, "amps_sent", 0) + len(items) * chunk
+        # the logical bits trade places (flip flags stay with the rank bits)
+        for gp, lp in pairs:
+            la, lb = self.phys.index(gp), self.phys.index(lp)
+            self.phys[la], self.phys[lb] = lp, gp
 
     # -- gathering (tests / small registers only) -----------------------------------------------------
     def gather_numpy(self) -> np.ndarray:
@@ -262,42 +294,66 @@ class ShardedState:
         local = torch.view_as_real(self._as_torch(self.buf)).contiguous()
         parts = [torch.empty_like(local) for _ in range(self.comm.size)]
         self.comm.dist.all_gather(parts, local, group=self.comm.group)
-        full = np.concatenate([torch.view_as_complex(p).cpu().numpy() for p in parts])   # physical order
+        flipmask = sum(f << i for i, f in enumerate(self.flip))
+        # rank r holds the logical rank value r ^ flipmask
+        full = np.concatenate([torch.view_as_complex(parts[r ^ flipmask]).cpu().numpy()
+                               for r in range(self.comm.size)])                         # physical order
         # physical index -> logical index: move physical bit phys[l] to logical bit l
         cube = full.reshape((2,) * self.n)                    # axis a <-> physical bit n-1-a
         axes = [self.n - 1 - self.phys[self.n - 1 - a] for a in range(self.n)]   # logical axis a takes that physical axis
         return np.ascontiguousarray(cube.transpose(axes)).reshape(-1)
 
 
+def _kind(bits, m: np.ndarray) -> str:
+    if _is_diagonal(m):
+        return "diag"
+    if len(bits) == 1 and m[0, 0] == 0 and m[1, 1] == 0:
+        return "anti"                                # relabels the ranks when it sits on a rank qubit
+    return "full"
+
+
 class ShardedSimulator:
-    """Runs a list of matrix gates (this package's ``Gate`` objects) on a ShardedState."""
+    """Runs a list of matrix gates (this package's ``Gate`` objects) on a ShardedState.
+
+    ``compile()`` builds the stage schedule; ``prepare(vectors)`` builds the product
+    state in the layout the first stage wants; ``run()`` executes."""
 
     def __init__(self, circuit, state: ShardedState, plan_options=None):
         self.circuit = circuit
         self.state = state
         self.plan_options = plan_options
-        self.stats = {"segments": 0, "passes": 0, "swaps": 0, "local_gates": 0}
+        self.stats = {"segments": 0, "passes": 0, "swaps": 0, "local_gates": 0, "exchange_units": 0.0,
+                      "relabels": 0}
+        self._schedule = None
+        self.initial_phys = list(range(state.n))
+        self.final_flip = [0] * state.g
 
     # ---- scheduling helpers ---------------------------------------------------------------------
     def _lower(self):
-        """[(logical_bits (factor order), matrix, is_diag)]"""
+        """[(logical_bits (factor order), matrix, kind)]"""
         n = self.state.n
         out = []
         for gate in self.circuit:
             for targets, matrix in gate.lowered(n, False):
                 m = np.asarray(matrix, dtype=np.complex128)
-                out.append(([n - 1 - q for q in targets], m, _is_diagonal(m)))
+                bits = [n - 1 - q for q in targets]
+                out.append((bits, m, _kind(bits, m)))
         return out
 
-    def _restrict_diagonal(self, bits_phys, matrix):
+    def _rank_value(self, phys_bit: int, flip) -> int:
+        st = self.state
+        i = phys_bit - st.n_local
+        return ((st.comm.rank >> i) & 1) ^ flip[i]
+
+    def _restrict_diagonal(self, bits_phys, matrix, flip):
         """Diagonal gate with some targets in the rank number: keep this rank's entries."""
         st = self.state
         k = len(bits_phys)
         diag = np.diagonal(matrix).reshape((2,) * k)
         index, local_bits = [], []
-        for f, p in enumerate(bits_phys):
+        for p in bits_phys:
             if p >= st.n_local:
-                index.append((st.comm.rank >> (p - st.n_local)) & 1)
+                index.append(self._rank_value(p, flip))
             else:
                 index.append(slice(None))
                 local_bits.append(p)
@@ -306,118 +362,123 @@ class ShardedSimulator:
             return [0], np.diag([sub[0], sub[0]])
         return local_bits, np.diag(sub)
 
+    @staticmethod
+    def _choose_rank_qubits(ops, pending, current, n, g):
+        """The g logical bits whose first blocking gate among ``pending`` lies farthest
+        ahead (never blocked at all is best); ties keep what is a rank qubit already."""
+        dist = {}
+        for pos, idx in enumerate(pending):
+            bits, _m, kind = ops[idx]
+            if kind == "full":
+                for b in bits:
+                    dist.setdefault(b, pos)
+        order = sorted(range(n), key=lambda l: (-dist.get(l, 1 << 60), 0 if l in current else 1, -l))
+        return set(order[:g])
+
     def compile(self):
-        """Walk the circuit once, tracking where every logical bit lives, and build
-        the schedule: fused local plans separated by global<->local swaps.  The
-        schedule starts from the identity layout (``set_product``)."""
+        """Cut the circuit into stages (see the module docstring) and build one fused
+        local plan per stage, separated by multi-qubit exchanges."""
         st = self.state
         ops = self._lower()
-        nloc = st.n_local
-        phys = list(range(st.n))                      # simulated layout
-        uses = {}
-        for idx, (bits, _m, is_diag) in enumerate(ops):
-            if not is_diag:
-                for b in bits:
-                    uses.setdefault(b, []).append(idx)
-        cursor = {b: 0 for b in uses}
-
-        def next_use(bit, now):
-            lst = uses.get(bit)
-            if not lst:
-                return 1 << 60
-            c = cursor[bit]
-            while c < len(lst) and lst[c] < now:
-                c += 1
-            cursor[bit] = c
-            return lst[c] if c < len(lst) else 1 << 60
-
+        n, g, nloc = st.n, st.g, st.n_local
+        x_gate = np.array([[0, 1], [1, 0]], dtype=np.complex128)
         schedule = []
 
-        def flush(segment):
-            if not segment:
-                return
-            plan = engine.Plan(st.backend, nloc, segment, self.plan_options)
-            schedule.append(("plan", plan))
-            self.stats["segments"] += 1
-            self.stats["passes"] += plan.stats["n_passes"]
-            self.stats["local_gates"] += len(segment)
+        pending = list(range(len(ops)))
+        # stage 0: the product state can be built in any layout, so choose before moving anything
+        glob = self._choose_rank_qubits(ops, pending, set(), n, g)
+        phys = [0] * n
+        for i, l in enumerate(sorted(glob)):
+            phys[l] = nloc + i
+        for i, l in enumerate(l for l in range(n) if l not in glob):
+            phys[l] = i
+        self.initial_phys = list(phys)
+        flip = [0] * g
+        carry = []                                   # logical bits that arrived complemented: X first
 
-        saved = st.phys
-        try:
-            st.phys = phys                             # _restrict_diagonal reads the layout
-            pending = list(range(len(ops)))
-            while pending:
-                # Classify what could run in the current layout.  A gate that cannot
-                # (non-diagonal on a rank bit) blocks its qubits; gates behind it are held
-                # back only if they do not commute with what is blocked (diagonal gates
-                # commute with each other).
-                ready, deferred = [], []
-                blocked_full, blocked_diag = set(), set()
-                for idx in pending:
-                    bits, m, is_diag = ops[idx]
-                    free = not (blocked_full & set(bits)) and (is_diag or not (blocked_diag & set(bits)))
-                    if free and (is_diag or all(phys[b] < nloc for b in bits)):
-                        ready.append(idx)
-                    else:
-                        deferred.append(idx)
-                        (blocked_diag if is_diag else blocked_full).update(bits)
+        while True:
+            # What can run in this layout.  A gate that cannot (neither diagonal nor a
+            # single-qubit antidiagonal, and on a rank qubit) blocks its qubits; gates behind it
+            # are held back only if they do not commute with what is blocked (diagonal gates
+            # commute with each other).
+            ready, deferred = [], []
+            blocked_full, blocked_diag = set(), set()
+            for idx in pending:
+                bits, _m, kind = ops[idx]
+                sb = set(bits)
+                is_diag = kind == "diag"
+                free = not (blocked_full & sb) and (is_diag or not (blocked_diag & sb))
+                if free and (kind != "full" or all(phys[b] < nloc for b in bits)):
+                    ready.append(idx)
+                else:
+                    deferred.append(idx)
+                    (blocked_diag if is_diag else blocked_full).update(bits)
 
-                def run_ops(indices):
-                    segment = []
-                    for idx in indices:
-                        bits, m, is_diag = ops[idx]
-                        p_bits = [phys[b] for b in bits]
-                        if is_diag and any(p >= nloc for p in p_bits):
-                            p_bits, m = self._restrict_diagonal(p_bits, m)
-                        segment.append(([nloc - 1 - p for p in p_bits], m))
-                    flush(segment)
+            segment = [([nloc - 1 - phys[l]], x_gate) for l in carry]
+            carry = []
+            for idx in ready:
+                bits, m, kind = ops[idx]
+                p_bits = [phys[b] for b in bits]
+                if kind == "diag" and any(p >= nloc for p in p_bits):
+                    p_bits, m = self._restrict_diagonal(p_bits, m, flip)
+                elif kind == "anti" and p_bits[0] >= nloc:
+                    v = self._rank_value(p_bits[0], flip)          # this rank's data becomes the 1-v branch
+                    scalar = m[1 - v, v]
+                    flip[p_bits[0] - nloc] ^= 1
+                    self.stats["relabels"] += 1
+                    p_bits, m = [0], np.diag([scalar, scalar])
+                segment.append(([nloc - 1 - p for p in p_bits], m))
+            if segment:
+                plan = engine.Plan(st.backend, nloc, segment, self.plan_options)
+                schedule.append(("plan", plan))
+                self.stats["segments"] += 1
+                self.stats["passes"] += plan.stats["n_passes"]
+                self.stats["local_gates"] += len(segment)
+            if not deferred:
+                break
 
-                def run_ready():
-                    run_ops(ready)
-                    ready.clear()
+            new_glob = self._choose_rank_qubits(ops, deferred, glob, n, g)
+            leaving = sorted(glob - new_glob, key=lambda l: phys[l])
+            entering = sorted(new_glob - glob, key=lambda l: phys[l])
+            assert leaving, "the scheduler made no progress"
+            pairs = [(phys[a], phys[b]) for a, b in zip(leaving, entering)]
+            schedule.append(("exchange", pairs))
+            self.stats["swaps"] += 1
+            self.stats["exchange_units"] += 1.0 - 0.5 ** len(pairs)
+            for a, b in zip(leaving, entering):
+                i = phys[a] - nloc
+                if flip[i]:                          # a's bit is stored complemented: fix it locally
+                    carry.append(a)
+                    flip[i] = 0
+                phys[a], phys[b] = phys[b], phys[a]
+            glob = new_glob
+            pending = deferred
 
-                if not deferred:
-                    run_ready()
-                    break
-                # Bring in the rank bits of the first blocked gate.  Ready gates are NOT run
-                # at every swap: gates that touch neither swapped qubit commute with the swap,
-                # so they keep accumulating into bigger, better-packed fused plans.  They must
-                # run first only if the evicted qubit still has a non-diagonal gate among them.
-                head = deferred[0]
-                bits = ops[head][0]
-                for b in bits:
-                    if phys[b] < nloc:
-                        continue
-                    busy = {}
-                    for idx in ready:
-                        if not ops[idx][2]:
-                            for q in ops[idx][0]:
-                                busy[q] = busy.get(q, 0) + 1
-                    local_logical = [l for l in range(st.n) if phys[l] < nloc and l not in bits]
-                    victim = max(local_logical, key=lambda l: (-busy.get(l, 0), next_use(l, head), phys[l]))
-                    if victim in busy:
-                        run_ready()       # (running only the closure of the victim's gates was
-                                          #  tried: many small, badly packed plans -- more passes)
-                    schedule.append(("swap", phys[b], phys[victim]))
-                    phys[b], phys[victim] = phys[victim], phys[b]
-                    self.stats["swaps"] += 1
-                pending = sorted(ready + deferred)
-        finally:
-            st.phys = saved
+        self.final_flip = list(flip)
+        self.final_phys = list(phys)
         self._schedule = schedule
         return schedule
 
-    def run(self) -> ShardedState:
-        """Execute the schedule on the state (which must be in the identity layout,
-        e.g. right after ``set_product``)."""
-        st = self.state
-        if getattr(self, "_schedule", None) is None:
+    def prepare(self, vectors) -> ShardedState:
+        """Product state (qubit 0 first) in the layout the first stage runs in."""
+        if self._schedule is None:
             self.compile()
-        if st.phys != list(range(st.n)):
-            raise ValueError("the schedule assumes the identity layout; call set_product first")
+        self.state.set_product(vectors, self.initial_phys)
+        return self.state
+
+    def run(self) -> ShardedState:
+        """Execute the schedule on the state, which must be in the schedule's initial
+        layout (``prepare``)."""
+        st = self.state
+        if self._schedule is None:
+            self.compile()
+        if st.phys != self.initial_phys or any(st.flip):
+            raise ValueError("the state is not in the schedule's initial layout; call prepare() first")
         for item in self._schedule:
             if item[0] == "plan":
                 item[1].execute(st.buf)
             else:
-                st.swap(item[1], item[2])
+                st.exchange(item[1])
+        assert st.phys == self.final_phys
+        st.flip = list(self.final_flip)
         return st

@@ -1,7 +1,8 @@
-"""Multi-rank path on CPU: world_size 2 and 4 over the gloo backend, every rank
-running the host emulator on its shard.  Checks the swap scheduling, the
-pack/unpack kernels' index arithmetic, the diagonal-gate restriction to rank
-bits and the final gather against the single-process oracle."""
+"""Multi-rank path on CPU: world_size 2, 4 and 8 over the gloo backend, every rank
+running the host emulator on its shard.  Checks the stage scheduling, the multi-qubit
+exchange (pack/unpack index arithmetic, pairing of the ranks), the diagonal-gate
+restriction to rank bits, the rank relabelling by antidiagonal gates (flip flags) and
+the final gather against the single-process oracle."""
 import os
 import socket
 import sys
@@ -36,18 +37,20 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
         from golden.specs import as_oracle_ops
         from oracle import strided
         from parity_cases import random_circuit
-        from quantum_computations_b200 import sharded, workloads
+        from quantum_computations_b200 import gates, sharded, workloads
         from quantum_computations_b200.states import State
 
         be = emu()
         comm = sharded.Comm()
         rng = np.random.default_rng(seed)                 # same circuit on every rank
         circ = workloads.sv_random_circuit(n, depth, seed) + random_circuit(n, 25, rng)
+        # leave every rank qubit complemented (and phased) at the end: the gather must undo it
+        circ += [gates.Y(q) for q in range(n)] + [gates.CZ(0, n - 1), gates.T(1)]
         vecs = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (n - 2)
         st = sharded.ShardedState(n, comm, backend=be, as_torch=torch.from_numpy)
-        st.set_product(vecs)
-        sharded.ShardedState.CHUNK_LOG2 = 5                 # several pipeline chunks per swap even at this size
+        sharded.ShardedState.CHUNK_LOG2 = 4                 # several pipeline chunks per block even at this size
         sim = sharded.ShardedSimulator(circ, st, plan_options=dict(tile_bits=6, low_bits=2))
+        sim.prepare(vecs)
         sim.run()
         nrm = st.norm()
         got = st.gather_numpy()
@@ -58,16 +61,59 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
             ref, _ = strided.run(as_oracle_ops(circ), psi0.astype(np.complex128))
             err = float(np.abs(got - ref).max() / np.abs(ref).max())
             np.save(os.path.join(out_dir, "result.npy"),
-                    np.array([err, nrm, np.linalg.norm(ref), sim.stats["swaps"], comm.bytes_exchanged]))
+                    np.array([err, nrm, np.linalg.norm(ref), sim.stats["swaps"], comm.bytes_exchanged,
+                              sim.stats["exchange_units"], sim.stats["relabels"]]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 9), (4, 10)])
+@pytest.mark.parametrize("world,n", [(2, 9), (4, 10), (8, 10)])
 def test_sharded_matches_oracle(tmp_path, world, n):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n, 6, 34, str(tmp_path)), nprocs=world, join=True)
-    err, nrm, ref_norm, swaps, nbytes = np.load(tmp_path / "result.npy")
+    err, nrm, ref_norm, swaps, nbytes, units, flips = np.load(tmp_path / "result.npy")
     assert err < 1e-12
     assert abs(nrm - ref_norm) < 1e-12
-    assert swaps > 0 and nbytes > 0                      # the global-qubit path was exercised
+    assert swaps > 0 and nbytes > 0                      # the rank-qubit path was exercised
+    assert flips > 0                                     # the relabelling path was exercised
+
+
+def _exchange_worker(rank, world, port, n, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emu_backend import emu
+        from quantum_computations_b200 import sharded
+
+        comm = sharded.Comm()
+        st = sharded.ShardedState(n, comm, backend=emu(), as_torch=torch.from_numpy)
+        sharded.ShardedState.CHUNK_LOG2 = 3
+        size = 1 << st.n_local
+        st.buf[:] = np.arange(rank * size, (rank + 1) * size) * (1 + 0.5j)   # psi[i] = i (1 + i/2), identity layout
+        want = np.arange(1 << n) * (1 + 0.5j)
+        bad = 0
+        nl, g = st.n_local, st.g
+        plans = [[(nl, 0)], [(nl + g - 1, nl - 1)], [(nl + i, 2 * i + 1) for i in range(g)],
+                 [(nl + i, nl - 2 - i) for i in range(g - 1, -1, -1)], [(nl, 3), (nl + g - 1, 0)][:g]]
+        for pairs in plans:
+            st.exchange(pairs)
+            if not np.array_equal(st.gather_numpy(), want):              # the logical state never changes
+                bad += 1
+        if rank == 0:
+            np.save(os.path.join(out_dir, "exchange.npy"), np.array([bad, st.swaps, sorted(st.phys) == list(range(n))]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 7), (4, 9), (8, 11)])
+def test_multi_qubit_exchange_is_a_bit_permutation(tmp_path, world, n):
+    """k rank bits <-> k local bits in one all-to-all (k = 1 .. log2 world): the data
+    moves, the logical state does not."""
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    bad, swaps, ok = np.load(tmp_path / "exchange.npy")
+    assert bad == 0 and swaps == 5 and ok
