@@ -5,7 +5,8 @@ top log2(N) qubits.  Default: 30 local qubits per GPU, i.e. 31 / 32 / 33 qubits 
 2 / 4 / 8 GPUs -- exactly the per-GPU state of the N = 1 bench, so the runs form a
 weak-scaling series; `--qubits 34` runs the 34-qubit case of BASELINE.json (31
 local qubits on 8 GPUs; recorded in profiles/).  Non-diagonal gates on a rank qubit
-trigger a global<->local swap (half a shard out and half a shard in per GPU).
+end a stage; between stages up to log2(N) rank qubits trade places with local ones in one
+all-to-all exchange (see quantum_computations_b200/sharded.py).
 
 A gate on an n-qubit register touches 2^n amplitudes, so gates/s alone is not
 comparable across register sizes: `value` is gates/s x 2^(n-30), the rate in units
@@ -55,7 +56,7 @@ def run_sharded(args, world, rank, local_rank):
     dist.barrier()
 
     launches0 = engine.launch_count(backend)
-    state.swap_seconds, state.swaps = 0.0, 0
+    state.swap_seconds, state.swaps, state.amps_sent = 0.0, 0, 0
     bytes0 = comm.bytes_exchanged
     total_ms = 0.0
     with ClockSampler(local_rank) as clocks:
@@ -83,8 +84,8 @@ def run_sharded(args, world, rank, local_rank):
         compute_ms = (ms_per_step - swap_ms * swaps) / max(1, passes)
         shard_bytes = 16.0 * 2.0 ** state.n_local
         achieved = 2.0 * shard_bytes / (compute_ms * 1e-3) / 1e9
-        half_bytes = shard_bytes / 2
-        nvlink = half_bytes / (swap_ms * 1e-3) / 1e9 if swaps else None
+        sent_bytes = 16.0 * getattr(state, "amps_sent", 0) / max(1, state.swaps)   # mean per exchange and GPU
+        nvlink = sent_bytes / (swap_ms * 1e-3) / 1e9 if swaps else None
         raw = args.steps * ngates / (total_ms * 1e-3)
         line = {
             "metric": METRIC, "value": raw * 2.0 ** (n - 30), "unit": "gates/s",
@@ -102,10 +103,12 @@ def run_sharded(args, world, rank, local_rank):
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": 2.0 * shard_bytes, "launches_per_step": passes,
                          "mean_launch_ms": compute_ms},
-            "swap": {"count_per_step": swaps, "mean_ms": swap_ms, "bytes_each_way_per_gpu": half_bytes,
+            "swap": {"count_per_step": swaps, "mean_ms": swap_ms, "bytes_each_way_per_gpu": sent_bytes,
+                     "shard_fraction_sent": sent_bytes / shard_bytes,
                      "achieved_GBps_per_direction": nvlink, "peak_GBps_measured_peer_copy": 770.0,
                      "peak_GBps_nominal": 900.0, "frac_of_measured": (nvlink / 770.0) if nvlink else None,
-                     "note": "host-timed with a device synchronize on both sides of every swap"},
+                     "note": "one exchange = k rank qubits <-> k local qubits in one all-to-all (1 - 2^-k of the "
+                             "shard leaves each GPU); host-timed with a device synchronize on both sides"},
             "cpu_baseline": None,
             "e2e": {"value": raw * 2.0 ** (n - 30), "unit": "gates/s",
                     "h2d_bytes_per_step": 25288 * passes + 64 * n, "d2h_bytes_per_step": 16,

@@ -45,6 +45,12 @@ typedef struct {
   int32_t max_dense_ops;    /* cap on non-diagonal gates per pass;                 0 = default  */
   int32_t lookahead;        /* gates scanned ahead when choosing a tile;           0 = default  */
   int32_t merge_1q;         /* 0 = default (on), 1 = on, 2 = off                                */
+  int32_t defer_tail;       /* 1 = do not apply the trailing diagonal / antidiagonal single-qubit
+                               products; hand them back through qsim_plan_residual so that the
+                               caller can merge them into its next plan (needs merge_1q on)      */
+  int32_t reserved0;
+  uint64_t apply_tail_mask; /* with defer_tail: qubits (bit q = qubit q) whose trailing products are
+                               applied all the same                                              */
 } qsim_plan_options_t;
 
 typedef struct {
@@ -77,6 +83,10 @@ int qsim_plan_compile(const qsim_circuit_t* c, const qsim_plan_options_t* opt, q
 int qsim_plan_stats(const qsim_plan_t* p, qsim_plan_stats_t* out);
 /* scratch: device buffer of 2^n amplitudes, needed only when stats.n_generic > 0 */
 int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void* stream);
+/* With options.defer_tail: the single-qubit gate left over on every qubit, n_qubits x (2x2
+ * row-major complex) = 8 doubles per qubit, qubit 0 first; identity where nothing is left.
+ * The state after qsim_plan_execute followed by these gates equals the circuit's. */
+int qsim_plan_residual(const qsim_plan_t* p, double* out);
 void qsim_plan_destroy(qsim_plan_t* p);
 
 /* ---- single operations (each is a one-gate plan) ------------------------------- */

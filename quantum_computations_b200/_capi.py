@@ -21,6 +21,9 @@ class PlanOptions(C.Structure):
         ("max_dense_ops", C.c_int32),
         ("lookahead", C.c_int32),
         ("merge_1q", C.c_int32),
+        ("defer_tail", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("apply_tail_mask", C.c_uint64),
     ]
 
 
@@ -53,6 +56,7 @@ SIGNATURES = {
     "qsim_plan_compile": (C.c_int, [C.c_void_p, C.POINTER(PlanOptions), c_void_pp]),
     "qsim_plan_stats": (C.c_int, [C.c_void_p, C.POINTER(PlanStats)]),
     "qsim_plan_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "qsim_plan_residual": (C.c_int, [C.c_void_p, c_double_p]),
     "qsim_plan_destroy": (None, [C.c_void_p]),
     "qsim_apply_matrix": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, c_double_p, C.c_void_p, C.c_void_p]),
     "qsim_apply_diagonal": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, c_double_p, C.c_void_p]),

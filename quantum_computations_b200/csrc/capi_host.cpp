@@ -74,7 +74,11 @@ int qsim_plan_compile(const qsim_circuit_t* c, const qsim_plan_options_t* opt, q
   int rc;
   try {
     if (o.merge_1q == 1) {
-      std::vector<qs::Op> merged = qs::merge_single_qubit(c->n, c->ops);
+      uint64_t apply_bits = 0;                       // option mask is by qubit; qubit q is index bit n-1-q
+      for (int q = 0; q < c->n; ++q)
+        if (o.apply_tail_mask >> q & 1) apply_bits |= 1ull << (c->n - 1 - q);
+      std::vector<qs::Op> merged =
+          qs::merge_single_qubit(c->n, c->ops, o.defer_tail == 1 ? &p->residual : nullptr, apply_bits);
       rc = qs::build_plan(c->n, merged, o, p);
     } else {
       rc = qs::build_plan(c->n, c->ops, o, p);
@@ -94,6 +98,21 @@ int qsim_plan_compile(const qsim_circuit_t* c, const qsim_plan_options_t* opt, q
 int qsim_plan_stats(const qsim_plan_t* p, qsim_plan_stats_t* out) {
   if (!p || !out) return qs::fail(QSIM_ERR_ARG, "qsim_plan_stats: null argument");
   *out = p->stats;
+  return QSIM_OK;
+}
+
+int qsim_plan_residual(const qsim_plan_t* p, double* out) {
+  if (!p || !out) return qs::fail(QSIM_ERR_ARG, "qsim_plan_residual: null argument");
+  for (int q = 0; q < p->n; ++q) {
+    double* dst = out + (size_t)8 * q;
+    if (p->residual.empty()) {
+      for (int e = 0; e < 8; ++e) dst[e] = 0.0;
+      dst[0] = 1.0; dst[6] = 1.0;
+    } else {
+      const double* src = p->residual.data() + (size_t)8 * (p->n - 1 - q);   // qubit q is index bit n-1-q
+      for (int e = 0; e < 8; ++e) dst[e] = src[e];
+    }
+  }
   return QSIM_OK;
 }
 

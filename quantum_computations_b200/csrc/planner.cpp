@@ -34,6 +34,7 @@ qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   if (o.max_dense_ops <= 0) o.max_dense_ops = 16;
   if (o.lookahead <= 0) o.lookahead = 600;
   if (o.merge_1q <= 0) o.merge_1q = 1;
+  if (o.defer_tail != 1 || o.merge_1q != 1) o.defer_tail = 0;
   if (o.tile_bits > QS_MAX_T) o.tile_bits = QS_MAX_T;
   if (o.max_group > QS_MAX_R) o.max_group = QS_MAX_R;
   if (o.low_bits + QS_MAX_R > o.tile_bits) o.low_bits = o.tile_bits - QS_MAX_R;
@@ -143,7 +144,8 @@ struct BitTrack {
 };
 }  // namespace
 
-std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
+std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector<double>* residual,
+                                   uint64_t apply_mask) {
   std::vector<Op> out;
   out.reserve(in.size());
   std::vector<BitTrack> tr(n);
@@ -261,9 +263,23 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in) {
       }
     }
   }
+  if (residual) residual->assign((size_t)8 * n, 0.0);
   for (int b = 0; b < n; ++b) {
-    emit_pending(b);        // a general gate leaves its left phases pending ...
-    emit_pending(b);        // ... which go out as a diagonal gate
+    if (!residual || (apply_mask >> b & 1)) {
+      emit_pending(b);      // a general gate leaves its left phases pending ...
+      emit_pending(b);      // ... which go out as a diagonal gate
+      if (residual) { (*residual)[(size_t)8 * b] = 1.0; (*residual)[(size_t)8 * b + 6] = 1.0; }
+      continue;
+    }
+    BitTrack& t = tr[b];
+    if (t.has_pending && !t.pending_diag && !is_antidiagonal(t.pending)) emit_pending(b);
+    double* r = residual->data() + (size_t)8 * b;
+    if (t.has_pending) {
+      for (int e = 0; e < 4; ++e) { r[2 * e] = t.pending[e].real(); r[2 * e + 1] = t.pending[e].imag(); }
+      t.has_pending = false;
+    } else {
+      r[0] = 1.0; r[6] = 1.0;
+    }
   }
   return out;
 }

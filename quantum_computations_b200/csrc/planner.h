@@ -50,6 +50,7 @@ struct qsim_circuit {
 struct qsim_plan {
   int n = 0;
   std::vector<qs::PlanItem> items;
+  std::vector<double> residual;          // n x 8 doubles (index bit b first), empty unless defer_tail
   qsim_plan_stats_t stats{};
 };
 
@@ -59,7 +60,11 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
 // Single-qubit merging pre-pass (returns the reduced op list).
-std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in);
+// With `residual` the trailing diagonal / antidiagonal product of every index bit is not
+// emitted but written there (8 doubles per bit, identity where nothing is pending).
+// Index bits in `apply_mask` are exempt.
+std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector<double>* residual = nullptr,
+                                   uint64_t apply_mask = 0);
 
 // Greedy tile/pass construction.
 int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt, qsim_plan* out);

@@ -27,7 +27,7 @@ if os.environ.get("QSIM_LIB"):          # development: try an experimental build
 
 # Planner knobs (0 = library default); bench.py sweeps these.
 PLAN_OPTIONS = {"tile_bits": 0, "low_bits": 0, "max_group": 0, "max_dense_ops": 0, "lookahead": 0,
-                "merge_1q": 0}
+                "merge_1q": 0, "defer_tail": 0, "apply_tail_mask": 0}
 
 
 def _as_c128(arr) -> np.ndarray:
@@ -190,6 +190,19 @@ class Plan:
         st = _capi.PlanStats()
         _capi.check(lib, lib.qsim_plan_stats(self._plan, C.byref(st)))
         self.stats = st.as_dict()
+
+    def residual_array(self) -> np.ndarray:
+        """With the ``defer_tail`` option: the diagonal / antidiagonal single-qubit gate the
+        plan left unapplied on every qubit, shape (n, 2, 2); identities elsewhere."""
+        out = np.zeros((self.n_bits, 2, 2), dtype=np.complex128)
+        _capi.check(self.backend.lib, self.backend.lib.qsim_plan_residual(self._plan, _dptr(out.view(np.float64))))
+        return out
+
+    def residual(self):
+        """``residual_array`` as ``[(qubit, 2x2 matrix), ...]`` without the identities."""
+        out = self.residual_array()
+        eye = np.eye(2)
+        return [(q, out[q]) for q in range(self.n_bits) if not np.array_equal(out[q], eye)]
 
     def execute(self, buf, scratch=None) -> None:
         be = self.backend

@@ -67,6 +67,11 @@ class Comm:
             req.wait()
         self.bytes_exchanged += s.numel() * s.element_size()
 
+    def allgather_object(self, obj) -> list:
+        out = [None] * self.size
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
     def allreduce_sum(self, values: np.ndarray) -> np.ndarray:
         import torch
         t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64))
@@ -323,7 +328,7 @@ class ShardedSimulator:
         self.state = state
         self.plan_options = plan_options
         self.stats = {"segments": 0, "passes": 0, "swaps": 0, "local_gates": 0, "exchange_units": 0.0,
-                      "relabels": 0}
+                      "relabels": 0, "carried_common": 0, "carried_signs": 0, "carried_controlled": 0}
         self._schedule = None
         self.initial_phys = list(range(state.n))
         self.final_flip = [0] * state.g
@@ -362,11 +367,92 @@ class ShardedSimulator:
             return [0], np.diag([sub[0], sub[0]])
         return local_bits, np.diag(sub)
 
+    defer_tails = True      # leave each stage's trailing single-qubit phases to the next stage's plan
+
+    def _carry_controlled(self, out, leaving, l, mats):
+        """The general case: a single-qubit gate on ``l`` selected by the ``leaving`` qubits."""
+        k = len(leaving)
+        full = np.zeros((2 << k, 2 << k), dtype=np.complex128)
+        for x, m in enumerate(mats):
+            full[2 * x:2 * x + 2, 2 * x:2 * x + 2] = m
+        out.append((list(leaving) + [l], full))
+        self.stats["carried_controlled"] += 1
+
+    def _carry_residuals(self, residual, leaving, leaving_phys, phys):
+        """Gates that stand for the unapplied leftovers (``qsim_plan_residual``) of the plan
+        before an exchange, as ``[(logical bits, matrix)]`` for the next stage.
+
+        The leftovers differ from rank to rank (restricted diagonals depend on the rank
+        bits), and after the exchange a shard holds data from all 2^k ranks of its group:
+        the amplitudes whose now-local qubits ``leaving`` read x came from the rank whose
+        bits ``leaving_phys`` were x.  So the leftover on a qubit is a gate controlled by the
+        ``leaving`` qubits.  Almost always the 2^k versions differ by scalars only (left
+        phases of the same rotation) or by a Z as well (a trailing CZ with a rank qubit): then
+        one common 2x2 goes to the qubit, the scalars collect into a single k-qubit diagonal and
+        the Z's come back as the CZ gates they were; otherwise the qubit gets its own
+        (k+1)-qubit gate, block diagonal in the ``leaving`` qubits.  Qubits that become rank
+        qubits in this exchange have nothing left over (``apply_tail_mask``)."""
+        st = self.state
+        nloc, k = st.n_local, len(leaving)
+        gather = getattr(st.comm, "allgather_object", None)
+        everyone = gather(residual) if gather else [residual] * st.comm.size     # (ranks, nloc, 2, 2)
+        sources = []
+        for x in range(1 << k):                       # x: factor order = `leaving` order, first most significant
+            r = st.comm.rank
+            for i, gp in enumerate(leaving_phys):
+                bit = (x >> (k - 1 - i)) & 1
+                r = (r & ~(1 << (gp - nloc))) | (bit << (gp - nloc))
+            sources.append(everyone[r])
+        where = {p: l for l, p in enumerate(phys)}
+        eye = np.eye(2)
+        x_gate = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+        cz_gate = np.diag([1, 1, 1, -1]).astype(np.complex128)
+        scalars = np.ones(1 << k, dtype=np.complex128)
+        out = []
+        for q in range(nloc):
+            mats = [src[q] for src in sources]
+            if all(np.array_equal(m, eye) for m in mats):
+                continue
+            l = where[nloc - 1 - q]
+            base = mats[0]
+            anti = base[0, 0] == 0 and base[1, 1] == 0
+            if any((m[0, 0] == 0 and m[1, 1] == 0) != anti for m in mats):
+                # H Z^v H = X^v: a rank-dependent Z between two gates turned into a bit flip
+                self._carry_controlled(out, leaving, l, mats)
+                continue
+            # the two non-zero entries: row 0 and row 1 (a Z on the qubit negates row 1)
+            top = [m[0, 1] if anti else m[0, 0] for m in mats]
+            bot = [m[1, 0] if anti else m[1, 1] for m in mats]
+            ratios = np.asarray([t / top[0] for t in top])                       # scalar per source rank
+            twist = np.asarray([(b / bot[0]) / r for b, r in zip(bot, ratios)])  # what is left on row 1
+            if np.allclose(twist, 1.0, rtol=0, atol=1e-14):
+                scalars *= ratios
+                out.append(([l], base))
+                self.stats["carried_common"] += 1
+                continue
+            # signs that are linear in x are CZ gates between the qubit and the `leaving` qubits
+            coeff = [int(np.real(twist[1 << (k - 1 - i)]) < 0) for i in range(k)]
+            linear = np.asarray([(-1.0) ** sum(c * ((x >> (k - 1 - i)) & 1) for i, c in enumerate(coeff))
+                                 for x in range(1 << k)])
+            if np.allclose(twist, linear, rtol=0, atol=1e-14):
+                scalars *= ratios
+                out.append(([l], base))
+                for i, c in enumerate(coeff):
+                    if c:
+                        out.append(([leaving[i], l], cz_gate))
+                self.stats["carried_signs"] += 1
+                continue
+            self._carry_controlled(out, leaving, l, mats)
+        if not np.array_equal(scalars, np.ones(1 << k)):
+            out.append((list(leaving), np.diag(scalars)))
+        return out
+
     @staticmethod
-    def _choose_rank_qubits(ops, pending, current, n, g):
+    def _choose_rank_qubits(ops, pending, current, n, g, local_now=()):
         """The g logical bits whose first blocking gate among ``pending`` lies farthest
-        ahead (never blocked at all is best); ties keep what is a rank qubit already."""
-        dist = {}
+        ahead (never blocked at all is best); ties keep what is a rank qubit already.
+        ``local_now``: bits that must be local in the next stage (progress guarantee)."""
+        dist = {b: -1 for b in local_now}
         for pos, idx in enumerate(pending):
             bits, _m, kind = ops[idx]
             if kind == "full":
@@ -394,7 +480,7 @@ class ShardedSimulator:
             phys[l] = i
         self.initial_phys = list(phys)
         flip = [0] * g
-        carry = []                                   # logical bits that arrived complemented: X first
+        carry = []                                   # [(logical bits, matrix)] to run before anything else
 
         while True:
             # What can run in this layout.  A gate that cannot (neither diagonal nor a
@@ -414,10 +500,13 @@ class ShardedSimulator:
                     deferred.append(idx)
                     (blocked_diag if is_diag else blocked_full).update(bits)
 
-            segment = [([nloc - 1 - phys[l]], x_gate) for l in carry]
-            carry = []
-            for idx in ready:
-                bits, m, kind = ops[idx]
+            head = deferred[0] if deferred else None          # the first gate that could not run
+
+            # carried gates first: X fix-ups of qubits that arrived complemented and the
+            # diagonal / antidiagonal leftovers of the previous plan (qsim_plan_residual)
+            segment = []
+
+            def emit(bits, m, kind):
                 p_bits = [phys[b] for b in bits]
                 if kind == "diag" and any(p >= nloc for p in p_bits):
                     p_bits, m = self._restrict_diagonal(p_bits, m, flip)
@@ -428,27 +517,46 @@ class ShardedSimulator:
                     self.stats["relabels"] += 1
                     p_bits, m = [0], np.diag([scalar, scalar])
                 segment.append(([nloc - 1 - p for p in p_bits], m))
+
+            for bits, m in carry:
+                emit(bits, m, _kind(bits, m))
+            carry = []
+            for idx in ready:
+                emit(*ops[idx])
+            # the next stage's rank qubits are chosen before this stage's plan is built: a qubit
+            # that is about to become a rank qubit must not leave anything unapplied behind
+            if deferred:
+                new_glob = self._choose_rank_qubits(ops, deferred, glob, n, g, ops[head][0])
+                leaving = sorted(glob - new_glob, key=lambda l: phys[l])
+                entering = sorted(new_glob - glob, key=lambda l: phys[l])
+                assert leaving, "the scheduler made no progress"
+                pairs = [(phys[a], phys[b]) for a, b in zip(leaving, entering)]
+            want_residual = bool(deferred) and self.defer_tails      # the same on every rank
+            residual = np.tile(np.eye(2, dtype=np.complex128), (nloc, 1, 1)) if want_residual else None
             if segment:
-                plan = engine.Plan(st.backend, nloc, segment, self.plan_options)
+                options = dict(self.plan_options or {})
+                if want_residual:
+                    options["defer_tail"] = 1
+                    options["apply_tail_mask"] = sum(1 << (nloc - 1 - lp) for _gp, lp in pairs)
+                plan = engine.Plan(st.backend, nloc, segment, options)
                 schedule.append(("plan", plan))
                 self.stats["segments"] += 1
                 self.stats["passes"] += plan.stats["n_passes"]
                 self.stats["local_gates"] += len(segment)
+                if want_residual:
+                    residual = plan.residual_array()
             if not deferred:
                 break
 
-            new_glob = self._choose_rank_qubits(ops, deferred, glob, n, g)
-            leaving = sorted(glob - new_glob, key=lambda l: phys[l])
-            entering = sorted(new_glob - glob, key=lambda l: phys[l])
-            assert leaving, "the scheduler made no progress"
-            pairs = [(phys[a], phys[b]) for a, b in zip(leaving, entering)]
+            if residual is not None:
+                carry = self._carry_residuals(residual, leaving[:len(pairs)], [gp for gp, _lp in pairs], phys)
             schedule.append(("exchange", pairs))
             self.stats["swaps"] += 1
             self.stats["exchange_units"] += 1.0 - 0.5 ** len(pairs)
             for a, b in zip(leaving, entering):
                 i = phys[a] - nloc
                 if flip[i]:                          # a's bit is stored complemented: fix it locally
-                    carry.append(a)
+                    carry.append(([a], x_gate))
                     flip[i] = 0
                 phys[a], phys[b] = phys[b], phys[a]
             glob = new_glob

@@ -285,6 +285,39 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
     return worst
 
 
+def check_deferred_tails(backend, trials, seed):
+    """options.defer_tail: the plan leaves trailing diagonal / antidiagonal single-qubit
+    products unapplied and reports them (qsim_plan_residual); plan + leftovers must equal
+    the circuit, and qubits in apply_tail_mask must have nothing left over."""
+    from quantum_computations_b200 import engine, workloads
+    rng = np.random.default_rng(seed)
+    seen = 0
+    for t in range(trials):
+        n = int(rng.integers(3, 11))
+        circ = workloads.sv_random_circuit(n, int(rng.integers(1, 6)), seed + t) + random_circuit(n, 6, rng)
+        ops = []
+        for g in circ:
+            ops.extend(g.lowered(n, False))
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        psi /= np.linalg.norm(psi)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        mask = int(rng.integers(0, 1 << n))
+        opts = dict(tile_bits=int(rng.integers(5, 9)), low_bits=2, defer_tail=1, apply_tail_mask=mask)
+        state = dev(psi, backend)
+        plan = engine.Plan(backend, n, ops, opts)
+        plan.execute(state.buf)
+        left = plan.residual()
+        for q, m in left:
+            assert not (mask >> q) & 1
+            assert (m[0, 1] == 0 and m[1, 0] == 0) or (m[0, 0] == 0 and m[1, 1] == 0)
+        seen += len(left)
+        if left:
+            engine.apply_lowered(state, [([q], m) for q, m in left], dict(tile_bits=opts["tile_bits"], low_bits=2))
+        err = rel_err(state.to_numpy(), ref)
+        assert err < RTOL, (n, opts, err)
+    assert seen > 0
+
+
 def check_dm_layers_vs_oracle(backend, n, depth, seed, db=10.0):
     """Config C3 at small N: noisy layered Clifford+T circuit on a density matrix."""
     noise = channels.GKPNoise(db)

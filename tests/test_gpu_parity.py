@@ -73,6 +73,10 @@ def test_random_vs_oracle_default_tiles(cuda_backend):
     pc.check_random_vs_oracle(cuda_backend, trials=12, n_range=(12, 18), tile_range=(10, 13), seed=22)
 
 
+def test_deferred_tails(cuda_backend):
+    pc.check_deferred_tails(cuda_backend, trials=30, seed=6)
+
+
 def test_dm_layers(cuda_backend):
     pc.check_dm_layers_vs_oracle(cuda_backend, n=4, depth=6, seed=12)
     pc.check_dm_layers_vs_oracle(cuda_backend, n=6, depth=4, seed=12)

@@ -25,6 +25,28 @@ def _free_port():
     return port
 
 
+def _leftover_circuit(gates, n, g):
+    """Qubits 0..g-1 see only diagonal gates for a while, so the scheduler makes them the
+    rank qubits; the other qubits end their first stage with leftovers that depend on the
+    rank bits in all three ways: a scalar (left phases after CZ . H), a sign (CZ after the
+    last H) and a bit flip (H . CZ . H)."""
+    circ = []
+    for q in range(g, n):
+        a = (q - g) % g
+        circ.append(gates.H(q))
+        circ.append(gates.T(q))
+        circ.append(gates.CZ(a, q))
+        if q % 3 == 0:
+            circ.append(gates.H(q))                    # H Z^v H = X^v
+        elif q % 3 == 1:
+            circ += [gates.RZ(q, 0.3 + q), gates.CZ((a + 1) % g, q)]
+        else:
+            circ += [gates.H(q), gates.T(q), gates.CZ((a + 1) % g, q)]
+    circ += [gates.T(a) for a in range(g)] + [gates.H(a) for a in range(g)]       # ends the stage
+    circ += [gates.H(q) for q in range(n)] + [gates.CZ(q, (q + 1) % n) for q in range(n)]
+    return circ
+
+
 def _worker(rank, world, port, n, depth, seed, out_dir):
     for p in (ROOT, HERE):
         if p not in sys.path:
@@ -43,7 +65,10 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
         be = emu()
         comm = sharded.Comm()
         rng = np.random.default_rng(seed)                 # same circuit on every rank
-        circ = workloads.sv_random_circuit(n, depth, seed) + random_circuit(n, 25, rng)
+        if depth == 0:
+            circ = _leftover_circuit(gates, n, world.bit_length() - 1)
+        else:
+            circ = workloads.sv_random_circuit(n, depth, seed) + random_circuit(n, 25, rng)
         # leave every rank qubit complemented (and phased) at the end: the gather must undo it
         circ += [gates.Y(q) for q in range(n)] + [gates.CZ(0, n - 1), gates.T(1)]
         vecs = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (n - 2)
@@ -62,7 +87,9 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
             err = float(np.abs(got - ref).max() / np.abs(ref).max())
             np.save(os.path.join(out_dir, "result.npy"),
                     np.array([err, nrm, np.linalg.norm(ref), sim.stats["swaps"], comm.bytes_exchanged,
-                              sim.stats["exchange_units"], sim.stats["relabels"]]))
+                              sim.stats["exchange_units"], sim.stats["relabels"],
+                              sim.stats["carried_common"], sim.stats["carried_controlled"],
+                              sim.stats["carried_signs"]]))
     finally:
         dist.destroy_process_group()
 
@@ -70,12 +97,14 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
 @pytest.mark.parametrize("world,n", [(2, 9), (4, 10), (8, 10)])
 def test_sharded_matches_oracle(tmp_path, world, n):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n, 6, 34, str(tmp_path)), nprocs=world, join=True)
-    err, nrm, ref_norm, swaps, nbytes, units, flips = np.load(tmp_path / "result.npy")
+    mp.spawn(_worker, args=(world, port, n, 12, 34, str(tmp_path)), nprocs=world, join=True)
+    err, nrm, ref_norm, swaps, nbytes, units, flips, common, controlled, signs = np.load(tmp_path / "result.npy")
+    print("exchanges", swaps, "units", units, "relabels", flips, "carried", common, signs, controlled)
     assert err < 1e-12
     assert abs(nrm - ref_norm) < 1e-12
     assert swaps > 0 and nbytes > 0                      # the rank-qubit path was exercised
     assert flips > 0                                     # the relabelling path was exercised
+    assert common > 0                                    # leftovers of a plan were carried across an exchange
 
 
 def _exchange_worker(rank, world, port, n, out_dir):
@@ -117,3 +146,17 @@ def test_multi_qubit_exchange_is_a_bit_permutation(tmp_path, world, n):
     mp.spawn(_exchange_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
     bad, swaps, ok = np.load(tmp_path / "exchange.npy")
     assert bad == 0 and swaps == 5 and ok
+
+
+@pytest.mark.parametrize("world,n", [(2, 8), (4, 9), (8, 10)])
+def test_leftovers_cross_an_exchange(tmp_path, world, n):
+    """What a stage's plan leaves unapplied (qsim_plan_residual) depends on the rank bits;
+    after the exchange it must come back as gates controlled by the qubits that were rank
+    qubits: scalars, signs (CZ) and bit flips (block-diagonal gate)."""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, 0, 5, str(tmp_path)), nprocs=world, join=True)
+    err, nrm, ref_norm, swaps, nbytes, units, flips, common, controlled, signs = np.load(tmp_path / "result.npy")
+    print("exchanges", swaps, "units", units, "carried", common, signs, controlled)
+    assert err < 1e-12
+    assert abs(nrm - ref_norm) < 1e-12
+    assert signs > 0 and controlled > 0                 # (the scalar-only case is covered by the random circuits)
