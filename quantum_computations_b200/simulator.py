@@ -66,6 +66,7 @@ class Simulator:
         self._backend = backend
         self._plan_options = plan_options
         self.last_stats: list[dict] = []
+        self._plans: dict = {}              # compiled plans of earlier runs, by content of the segment
 
     # -- helpers -----------------------------------------------------------------------
     def _initial(self, initial_state):
@@ -88,9 +89,35 @@ class Simulator:
         for gate in segment:
             ops.extend(gate.lowered(nq, dens))
             dtype = gate.result_dtype(nq, dtype)
-        self.last_stats.append(engine.apply_lowered(state, ops, self._plan_options))
+        self.last_stats.append(self._apply_cached(state, ops))
         state.host_dtype = dtype
         segment.clear()
+
+    _PLAN_CACHE_SIZE = 16
+
+    def _apply_cached(self, state, ops) -> dict:
+        """Like ``engine.apply_lowered``, but a plan compiled by an earlier ``run`` of this
+        simulator is reused when the segment is the same gate for gate (matrices compared
+        by value through a 128-bit digest, so mutating a gate between runs is safe)."""
+        import hashlib
+        from . import engine
+        if not ops:
+            return {}
+        h = hashlib.blake2b(digest_size=16)
+        h.update(repr((state.n_bits, id(state.backend), sorted((self._plan_options or {}).items()))).encode())
+        for targets, matrix in ops:
+            h.update(bytes(targets) if max(targets) < 256 else repr(targets).encode())
+            h.update(b"|")
+            h.update(np.ascontiguousarray(matrix, dtype=np.complex128).data)
+        key = h.digest()
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = engine.Plan(state.backend, state.n_bits, ops, self._plan_options)
+            if len(self._plans) >= self._PLAN_CACHE_SIZE:
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = plan
+        plan.execute(state.buf)
+        return plan.stats
 
     # -- public ---------------------------------------------------------------------------
     def run(self, initial_state=None, *, out: np.ndarray | None = None, return_device: bool = False):

@@ -285,6 +285,43 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
     return worst
 
 
+def check_plan_cache(backend):
+    """Simulator keeps compiled plans between runs, keyed by the content of the segment:
+    a second run must not plan again, and a gate mutated in between must be noticed."""
+    from quantum_computations_b200 import engine
+    n = 9
+    rng = np.random.default_rng(3)
+    circ = random_circuit(n, 60, rng)
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    sim = Simulator(circ, backend=backend)
+    made = []
+    real_plan = engine.Plan
+
+    class CountingPlan(real_plan):
+        def __init__(self, *a, **k):
+            made.append(1)
+            super().__init__(*a, **k)
+
+    engine.Plan = CountingPlan
+    try:
+        first = sim.run(psi)
+        n_first = len(made)
+        second = sim.run(psi)
+        assert len(made) == n_first and n_first >= 1
+        assert np.array_equal(first, second)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        assert rel_err(first, ref) < RTOL
+        k = next(i for i, g in enumerate(circ) if len(g.indices) == 1)
+        circ[k].matrix = np.asarray(circ[k].matrix) @ np.diag([1.0, 1j])
+        third = sim.run(psi)
+        assert len(made) > n_first
+        ref3, _ = strided.run(as_oracle_ops(circ), psi)
+        assert rel_err(third, ref3) < RTOL
+    finally:
+        engine.Plan = real_plan
+
+
 def check_deferred_tails(backend, trials, seed):
     """options.defer_tail: the plan leaves trailing diagonal / antidiagonal single-qubit
     products unapplied and reports them (qsim_plan_residual); plan + leftovers must equal

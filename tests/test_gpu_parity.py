@@ -73,6 +73,10 @@ def test_random_vs_oracle_default_tiles(cuda_backend):
     pc.check_random_vs_oracle(cuda_backend, trials=12, n_range=(12, 18), tile_range=(10, 13), seed=22)
 
 
+def test_plan_cache(cuda_backend):
+    pc.check_plan_cache(cuda_backend)
+
+
 def test_deferred_tails(cuda_backend):
     pc.check_deferred_tails(cuda_backend, trials=30, seed=6)
 
