@@ -31,7 +31,7 @@ qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   if (o.tile_bits <= 0) o.tile_bits = 12;
   if (o.low_bits <= 0) o.low_bits = 4;
   if (o.max_group <= 0) o.max_group = 3;
-  if (o.max_dense_ops <= 0) o.max_dense_ops = 16;
+  if (o.max_dense_ops <= 0) o.max_dense_ops = 20;
   if (o.lookahead <= 0) o.lookahead = 600;
   if (o.merge_1q <= 0) o.merge_1q = 1;
   if (o.defer_tail != 1 || o.merge_1q != 1) o.defer_tail = 0;
