@@ -63,6 +63,14 @@ int bind_device(const void* ptr, DevCtx** ctx) {
     QS_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks));
     QS_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 2));
     QS_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 2));
+    // stream-ordered allocations (generic-gate path) keep their memory between calls instead
+    // of handing it back to the driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, at.device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     c.ready = true;
   }
   *ctx = &c;
@@ -200,10 +208,43 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
 // =====================================================================================
 // Simple streaming kernels
 // =====================================================================================
-__global__ void k_init_product(qs_c128* state, int n, const double* __restrict__ amps, uint64_t count) {
+// the 2 x n single-qubit amplitudes travel as a kernel parameter (no allocation, no copy)
+struct ProductAmps { double a[4 * 40]; };
+
+__global__ void k_init_product(qs_c128* state, int n, const __grid_constant__ ProductAmps amps, uint64_t count) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
        i += (uint64_t)gridDim.x * blockDim.x)
-    state[i] = qs_product_amp(amps, n, i);
+    state[i] = qs_product_amp(amps.a, n, i);
+}
+
+// n >= 16: the index splits into (o2 | o1 | tid) = (bits 16.., bits 8..15, bits 0..7) and the
+// amplitude into three factors: one per thread (registers), a 256-entry table per block
+// (shared memory) and one per o2 (uniform) -- two complex multiplications per amplitude
+// instead of n, so the kernel runs at the HBM write rate.
+__device__ __forceinline__ qs_c128 product_bits(const ProductAmps& amps, int n, uint32_t v, int first_bit, int nbits) {
+  qs_c128 p; p.x = 1.0; p.y = 0.0;
+  for (int b = 0; b < nbits; ++b) {
+    const int q = n - 1 - (first_bit + b);
+    const int bit = (int)((v >> b) & 1u);
+    qs_c128 a; a.x = amps.a[4 * q + 2 * bit]; a.y = amps.a[4 * q + 2 * bit + 1];
+    p = qs_cmul(p, a);
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_init_product_big(qs_c128* state, int n, const __grid_constant__ ProductAmps amps) {
+  __shared__ qs_c128 t1[256];
+  const uint32_t tid = threadIdx.x;
+  const qs_c128 lo = product_bits(amps, n, tid, 0, 8);
+  t1[tid] = product_bits(amps, n, tid, 8, 8);
+  __syncthreads();
+  const uint64_t n2 = 1ull << (n - 16);
+  for (uint64_t o2 = blockIdx.x; o2 < n2; o2 += gridDim.x) {
+    const qs_c128 pl = qs_cmul(product_bits(amps, n, (uint32_t)o2, 16, n - 16), lo);
+    qs_c128* dst = state + (o2 << 16) + tid;
+#pragma unroll 4
+    for (uint32_t o1 = 0; o1 < 256; ++o1) dst[(uint64_t)o1 << 8] = qs_cmul(pl, t1[o1]);
+  }
 }
 
 struct BraPair { double b[4]; };
@@ -537,15 +578,19 @@ int qsim_init_product(void* state, int n_qubits, const double* amps, void* strea
   int rc = bind_device(state, &ctx);
   if (rc != QSIM_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  double* d_amps = nullptr;
-  const size_t bytes = sizeof(double) * 4 * n_qubits;
-  QS_CUDA(cudaMallocAsync(&d_amps, bytes, st));
-  QS_CUDA(cudaMemcpyAsync(d_amps, amps, bytes, cudaMemcpyHostToDevice, st));
+  ProductAmps pa;
+  memset(&pa, 0, sizeof(pa));
+  memcpy(pa.a, amps, sizeof(double) * 4 * n_qubits);
   const uint64_t count = 1ull << n_qubits;
-  k_init_product<<<stream_grid(ctx, count, 256), 256, 0, st>>>((qs_c128*)state, n_qubits, d_amps, count);
+  if (n_qubits >= 16) {
+    uint64_t blocks = count >> 16;
+    if (blocks > (uint64_t)ctx->sms * 8) blocks = (uint64_t)ctx->sms * 8;
+    k_init_product_big<<<(unsigned)blocks, 256, 0, st>>>((qs_c128*)state, n_qubits, pa);
+  } else {
+    k_init_product<<<stream_grid(ctx, count, 256), 256, 0, st>>>((qs_c128*)state, n_qubits, pa, count);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
-  QS_CUDA(cudaFreeAsync(d_amps, st));
   return QSIM_OK;
 }
 

@@ -73,6 +73,19 @@ def test_random_vs_oracle_default_tiles(cuda_backend):
     pc.check_random_vs_oracle(cuda_backend, trials=12, n_range=(12, 18), tile_range=(10, 13), seed=22)
 
 
+@pytest.mark.parametrize("n", [3, 15, 16, 17, 21])
+def test_product_state_matches_kron(cuda_backend, n):
+    """parse_state(list) (DV/simulator.py:26): the two product-state kernels (plain below
+    16 qubits, table-driven from 16 on) against numpy's kron of the same kets."""
+    rng = np.random.default_rng(n)
+    kets = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+    ref = np.ones(1, dtype=np.complex128)
+    for k in kets:
+        ref = np.kron(ref, k)
+    got = engine.DeviceState.product(list(kets), cuda_backend).to_numpy()
+    assert pc.rel_err(got, ref) < 1e-13
+
+
 def test_plan_cache(cuda_backend):
     pc.check_plan_cache(cuda_backend)
 
