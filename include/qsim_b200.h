@@ -76,6 +76,10 @@ int qsim_circuit_create(int n_qubits, qsim_circuit_t** out);
 /* Gate.apply ket branch, any k (DV/gates.py:48-50).  Structure (diagonal, CZ,
  * Z) is detected from the matrix values. */
 int qsim_circuit_add_matrix(qsim_circuit_t* c, int k, const int* targets, const double* matrix);
+/* `count` gates in one call: ks[g] qubits each, targets and row-major complex matrices
+ * concatenated in gate order (same checks as qsim_circuit_add_matrix, gate by gate). */
+int qsim_circuit_add_many(qsim_circuit_t* c, int64_t count, const int32_t* ks, const int32_t* targets,
+                          const double* matrices);
 int qsim_circuit_num_ops(const qsim_circuit_t* c);
 void qsim_circuit_destroy(qsim_circuit_t* c);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "qsim_has_cuda": (C.c_int, []),
     "qsim_circuit_create": (C.c_int, [C.c_int, c_void_pp]),
     "qsim_circuit_add_matrix": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_double_p]),
+    "qsim_circuit_add_many": (C.c_int, [C.c_void_p, C.c_int64, c_int_p, c_int_p, c_double_p]),
     "qsim_circuit_num_ops": (C.c_int, [C.c_void_p]),
     "qsim_circuit_destroy": (None, [C.c_void_p]),
     "qsim_plan_compile": (C.c_int, [C.c_void_p, C.POINTER(PlanOptions), c_void_pp]),

@@ -62,6 +62,20 @@ int qsim_circuit_add_matrix(qsim_circuit_t* c, int k, const int* targets, const 
   return QSIM_OK;
 }
 
+int qsim_circuit_add_many(qsim_circuit_t* c, int64_t count, const int32_t* ks, const int32_t* targets,
+                          const double* matrices) {
+  if (!c || count < 0 || (count > 0 && (!ks || !targets || !matrices)))
+    return qs::fail(QSIM_ERR_ARG, "qsim_circuit_add_many: null argument");
+  for (int64_t g = 0; g < count; ++g) {
+    const int k = ks[g];
+    const int rc = qsim_circuit_add_matrix(c, k, targets, matrices);
+    if (rc != QSIM_OK) return rc;
+    targets += k;
+    matrices += (size_t)2 << (2 * k);
+  }
+  return QSIM_OK;
+}
+
 int qsim_circuit_num_ops(const qsim_circuit_t* c) { return c ? (int)c->ops.size() : 0; }
 
 void qsim_circuit_destroy(qsim_circuit_t* c) { delete c; }

@@ -171,13 +171,19 @@ class Plan:
         circ = C.c_void_p()
         _capi.check(lib, lib.qsim_circuit_create(self.n_bits, C.byref(circ)))
         try:
-            for targets, matrix in ops:
+            # one call for the whole gate list (a ctypes call per gate costs more than planning)
+            ks = np.fromiter((len(t) for t, _m in ops), dtype=np.int32, count=len(ops))
+            mats = []
+            for (targets, matrix), k in zip(ops, ks):
                 m = _as_c128(matrix)
-                k = len(targets)
-                if m.shape != (2 ** k, 2 ** k):
+                if m.shape != (1 << k, 1 << k):
                     raise ValueError("Dimensions of given matrix is not compatible with number of indices.")
-                t = (C.c_int * k)(*[int(q) for q in targets])
-                _capi.check(lib, lib.qsim_circuit_add_matrix(circ, k, t, _dptr(m.view(np.float64))))
+                mats.append(m.reshape(-1))
+            flat_t = np.fromiter((int(q) for t, _m in ops for q in t), dtype=np.int32, count=int(ks.sum()))
+            flat_m = np.concatenate(mats) if mats else np.zeros(0, dtype=np.complex128)
+            _capi.check(lib, lib.qsim_circuit_add_many(
+                circ, len(ops), ks.ctypes.data_as(_capi.c_int_p), flat_t.ctypes.data_as(_capi.c_int_p),
+                _dptr(flat_m.view(np.float64))))
             merged = dict(PLAN_OPTIONS)
             if options:
                 merged.update(options)
