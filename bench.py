@@ -44,7 +44,7 @@ import numpy as np  # noqa: E402
 METRIC = "gates/sec (30q c128 random circuit, depth 200)"
 # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
 # `ncu --set full` capture summarised in profiles/r1_ncu_full_k_tile_pass_n30.csv (17.18 GB + 17.12 GB)
-NCU_TRAFFIC_N30 = 34.30e9
+NCU_TRAFFIC_N30 = 34.35e9
 
 
 def parse_args():

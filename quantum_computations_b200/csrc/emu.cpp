@@ -8,6 +8,7 @@
 // the plan logic and the index arithmetic without a GPU.  The product package
 // never loads it: quantum_computations_b200.engine binds libqsim_b200.so only
 // and raises when that library or a CUDA device is missing.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -400,6 +401,43 @@ int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, c
   const qs_c128* b = (const qs_c128*)recvbuf;
   for (uint64_t r = 0; r < count; ++r) s[qs_deposit(first + r, sel)] = b[r];
   ++g_launches;
+  return QSIM_OK;
+}
+
+// Test-only: shared-memory wavefronts of the 128-bit step accesses of a plan, as the
+// hardware serves them (8 lanes per wavefront; lanes conflict when their 16-byte slots
+// are equal mod 8).  out[0] = wavefronts, out[1] = the conflict-free minimum.
+int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
+  if (!p || !out) return qs::fail(QSIM_ERR_ARG, "qsim_emu_step_wavefronts: null argument");
+  double total = 0, ideal = 0;
+  for (const qs::PlanItem& it : p->items) {
+    if (it.generic) continue;
+    const QsPass& P = it.pass;
+    for (int s = 0; s < (int)P.nsteps; ++s) {
+      const QsStep& st = P.steps[s];
+      QsStepTab tab;
+      for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, QS_THREADS_LOG2);
+      const uint32_t nwork = 1u << (P.T - st.r);
+      for (uint32_t warp = 0; warp < QS_THREADS / 32; ++warp)
+        for (uint32_t i = 0, w0 = warp * 32; w0 < nwork; ++i, w0 += QS_THREADS)
+          for (int m = 0; m < (1 << st.r); ++m)
+            for (int quarter = 0; quarter < 4; ++quarter) {
+              int count[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
+              for (int l = 0; l < 8; ++l) {
+                const uint32_t tid = warp * 32 + quarter * 8 + l;
+                if (tid + i * QS_THREADS >= nwork) continue;
+                const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
+                const uint32_t slo = qs_swz(jlo);
+                const uint32_t byte = ((slo ^ (tab.hi[i] >> 16)) << 4) ^ tab.sdepb[m];
+                worst = std::max(worst, ++count[(byte >> 4) & 7u]);
+              }
+              total += worst;
+              ideal += worst ? 1 : 0;
+            }
+    }
+  }
+  out[0] = total;
+  out[1] = ideal;
   return QSIM_OK;
 }
 
