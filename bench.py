@@ -13,8 +13,10 @@ Reported on one JSON line:
   value      gates/s with the state resident in HBM and the fused plan compiled
              (the timed region is the tile-pass kernels only, CUDA events).
   e2e        gates/s through the public API ``Simulator(circuit).run([ZERO]*n, out=pinned)``:
-             host circuit objects in, lowering + planning + launches + the
-             device->host copy of the final 2^n amplitudes inside the timed region.
+             host circuit objects in; lowering, plan lookup (the plan compiled by the
+             warm-up run is reused through the simulator's content-keyed cache, compile
+             time is config.plan_seconds), product state, launches and the device->host
+             copy of the final 2^n amplitudes inside the timed region.
   roofline   k_tile_pass: algorithmic bytes per launch = 2 x 16 B x 2^n (one read and
              one write of the state) over the mean launch time, against the measured
              HBM copy bandwidth in MEASURED_PEAKS.json.
