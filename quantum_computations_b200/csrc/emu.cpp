@@ -9,6 +9,7 @@
 // never loads it: quantum_computations_b200.engine binds libqsim_b200.so only
 // and raises when that library or a CUDA device is missing.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -410,10 +411,13 @@ int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, c
 int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
   if (!p || !out) return qs::fail(QSIM_ERR_ARG, "qsim_emu_step_wavefronts: null argument");
   double total = 0, ideal = 0;
+  int pass_no = 0;
   for (const qs::PlanItem& it : p->items) {
     if (it.generic) continue;
     const QsPass& P = it.pass;
+    ++pass_no;
     for (int s = 0; s < (int)P.nsteps; ++s) {
+      const double t_before = total, i_before = ideal;
       const QsStep& st = P.steps[s];
       QsStepTab tab;
       for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, QS_THREADS_LOG2);
@@ -434,6 +438,13 @@ int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
               total += worst;
               ideal += worst ? 1 : 0;
             }
+      if (getenv("QSIM_EMU_VERBOSE") && total - t_before > 1.01 * (ideal - i_before)) {
+        fprintf(stderr, "pass %d step %d r %d ratio %.2f gpos", pass_no, s, st.r, (total - t_before) / (ideal - i_before));
+        for (int f = 0; f < st.r; ++f) fprintf(stderr, " %d", st.gpos[f]);
+        fprintf(stderr, " fpos");
+        for (int f = 0; f < (int)P.T - st.r; ++f) fprintf(stderr, " %d", st.fpos[f]);
+        fprintf(stderr, " sync %d\n", st.block_sync);
+      }
     }
   }
   out[0] = total;

@@ -632,9 +632,47 @@ void assign_runs(QsPass& P) {
       ++s;
       continue;
     }
+    // Warp-owned positions: any QS_WARP_BITS positions that no step of the run uses as a
+    // group bit.  Prefer a choice that leaves every step three lane positions with different
+    // residues mod 3 (conflict-free 128-bit accesses under the XOR-fold swizzle, tile_exec.h);
+    // the highest positions otherwise.
     int wp[4], nw = 0;
-    for (int p = T - 1; p >= 0 && nw < QS_WARP_BITS; --p)
-      if (!(used >> p & 1)) wp[nw++] = p;
+    {
+      int cand[QS_MAX_T], nc = 0;
+      for (int p = T - 1; p >= 0; --p)
+        if (!(used >> p & 1)) cand[nc++] = p;
+      auto steps_ok = [&](uint32_t wmask) {          // steps of the run left conflict-free
+        int ok = 0;
+        for (int i = s; i < e; ++i) {
+          uint32_t g = 0;
+          for (int f = 0; f < P.steps[i].r; ++f) g |= 1u << P.steps[i].gpos[f];
+          int have = 0;
+          for (int p = 0; p < T; ++p)
+            if (!((g | wmask) >> p & 1)) have |= 1 << (p % 3);
+          ok += have == 7;
+        }
+        return ok;
+      };
+      bool found = false;
+      if (QS_WARP_BITS == 3 && nc >= 3) {
+        int best = -1;
+        for (int a = 0; a < nc; ++a)
+          for (int b = a + 1; b < nc; ++b)
+            for (int c = b + 1; c < nc; ++c) {
+              const int ok = steps_ok((1u << cand[a]) | (1u << cand[b]) | (1u << cand[c]));
+              if (ok > best) {                      // candidates come highest positions first
+                best = ok;
+                wp[0] = cand[a]; wp[1] = cand[b]; wp[2] = cand[c];
+                nw = 3;
+                found = true;
+              }
+            }
+      }
+      if (!found) {
+        nw = 0;
+        for (int i = 0; i < nc && nw < QS_WARP_BITS; ++i) wp[nw++] = cand[i];
+      }
+    }
     for (int i = s; i < e; ++i) {
       order_free_positions(P.steps[i], T, wp, QS_WARP_BITS);
       P.steps[i].block_sync = (i == e - 1) ? 1 : 0;
