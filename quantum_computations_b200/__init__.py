@@ -17,6 +17,7 @@ plus what the hot path needs on a GPU:
     trajectories    Pauli-trajectory sampling of noisy circuits on kets
     layering        measurement-based layer scheduling           (GKP/circuit.py)
     cliffords       two-qubit Clifford table and Clifford RB    (PAPER/average_clifford_fidelity.py)
+    tomography      process tomography, Kraus fit of a circuit   (PAPER/tomography.py)
     compat          ``install()`` exposes the package as ``simulators.dv_simulator``
 
 Importing the package is cheap and needs neither torch nor a GPU; the CUDA

@@ -360,8 +360,46 @@ def gen_layering():
     print(f"wrote layering.json: {len(cases)} cases")
 
 
+def gen_tomography():
+    """Process tomography with the reference's own tomography.py: random CPTP channels on 1
+    and 2 qubits -> process matrix, chi matrix, eigenvalues, and the recovered Kraus set's
+    action on a fresh state; plus the reference's bases."""
+    import tomography as ptomo     # PAPER/tomography.py
+    rng = np.random.default_rng(808)
+    meta, arrays = [], {}
+    for N, nk in ((1, 1), (1, 3), (2, 2), (2, 5)):
+        dim = 2 ** N
+        iso = np.linalg.qr(rng.normal(size=(nk * dim, dim)) + 1j * rng.normal(size=(nk * dim, dim)))[0]
+        ks = [iso[dim * i:dim * (i + 1), :] for i in range(nk)]
+        process = ptomo.quantum_channel(ks, ket_input=True, return_input=True)
+        inputs, outputs = ptomo.eval_process(process, N, True)
+        M = ptomo.process_matrix(inputs, outputs)
+        chi = ptomo.chi_matrix(M, N)
+        D, Ks = ptomo.krauss_operators(chi, N)
+        fitted = ptomo.process_tomography(process, N)
+        probe = rand_rho(N, rng)
+        tag = f"c{len(meta)}"
+        arrays[tag + "_kraus"] = np.stack(ks)
+        arrays[tag + "_inputs"] = np.stack(inputs)
+        arrays[tag + "_outputs"] = np.stack(outputs)
+        arrays[tag + "_M"] = M
+        arrays[tag + "_chi"] = chi
+        arrays[tag + "_D"] = D
+        arrays[tag + "_probe"] = probe
+        arrays[tag + "_probe_out"] = ptomo.quantum_channel(fitted)(probe)
+        meta.append({"tag": tag, "N": N, "n_kraus": nk, "n_fitted": len(fitted)})
+    for N in (1, 2):
+        arrays[f"state_basis{N}"] = np.stack(ptomo.state_basis(N))
+        arrays[f"pure_kets{N}"] = np.stack(ptomo.pure_state_basis_kets(N))
+        arrays[f"operator_basis{N}"] = np.stack(ptomo.operator_basis(N))
+    save("tomography.npz", meta, arrays)
+
+
 if __name__ == "__main__":
     fast = "--fast" in sys.argv
+    if "--only-tomography" in sys.argv:
+        gen_tomography()
+        sys.exit(0)
     gen_single_gates()
     gen_density_gates()
     gen_measure()
@@ -374,3 +412,4 @@ if __name__ == "__main__":
     gen_sim_measure()
     gen_circuits(fast)
     gen_layering()
+    gen_tomography()

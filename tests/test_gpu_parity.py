@@ -86,6 +86,24 @@ def test_product_state_matches_kron(cuda_backend, n):
     assert pc.rel_err(got, ref) < 1e-13
 
 
+def test_tomography_of_a_noisy_gate(cuda_backend):
+    """SURVEY 8f rank 4 on the device: fit the Kraus operators of H and CZ with their GKP noise
+    channels from density-matrix simulations of the 4^N probe states."""
+    from quantum_computations_b200 import channels, tomography as tomo
+    from quantum_computations_b200 import numpy_quantum as npq
+    noise = channels.GKPNoise(10.0)
+    for circuit, n in (([gates.H(0)], 1), ([gates.H(1), gates.CZ(0, 1)], 2)):
+        fitted = tomo.circuit_kraus(circuit, n, noise=noise, backend=cuda_backend)
+        want = np.eye(4 ** n, dtype=complex)
+        for g in circuit:
+            u = np.asarray(npq.expand_gate(np.asarray(g.matrix, dtype=complex), n, list(g.indices)))
+            want = np.kron(u, np.conjugate(u)) @ want
+            for q, (px, pz) in zip(g.indices, noise.flips_for(g)):
+                ks = [np.asarray(npq.expand_gate(np.asarray(k, dtype=complex), n, [q])) for k in noise.pauli_kraus(px, pz)]
+                want = tomo.superoperator(ks) @ want
+        assert np.abs(tomo.superoperator(fitted) - want).max() < 1e-12
+
+
 def test_plan_cache(cuda_backend):
     pc.check_plan_cache(cuda_backend)
 
