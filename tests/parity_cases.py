@@ -285,6 +285,52 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
     return worst
 
 
+def check_swap_pack_unpack(backend):
+    """qsim_swap_pack / _unpack (the gather / scatter of a k-qubit exchange block) against
+    NumPy indexing, chunked like the pipeline does."""
+    import ctypes as C
+    from quantum_computations_b200 import _capi
+    rng = np.random.default_rng(17)
+    n = 11
+    lib = backend.lib
+    for trial in range(12):
+        k = int(rng.integers(1, 5))
+        qubits = [int(q) for q in rng.choice(n, size=k, replace=False)]
+        values = [int(v) for v in rng.integers(0, 2, size=k)]
+        shard = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        # reference: amplitudes whose qubit q (bit n-1-q) equals its value, in index order
+        idx = np.arange(2 ** n)
+        sel = np.ones(2 ** n, dtype=bool)
+        for q, v in zip(qubits, values):
+            sel &= ((idx >> (n - 1 - q)) & 1) == v
+        want = shard[sel]
+        block = 2 ** (n - k)
+        assert want.size == block
+        d_shard = backend.upload(shard)
+        d_buf = backend.upload(np.zeros(block, dtype=np.complex128))
+        cq, cv = (C.c_int * k)(*qubits), (C.c_int * k)(*values)
+        chunk = block // 4 if block >= 4 else block
+        for first in range(0, block, chunk):
+            _capi.check(lib, lib.qsim_swap_pack(backend.ptr(d_shard), backend.ptr(d_buf), n, k, cq, cv,
+                                                C.c_uint64(first), C.c_uint64(chunk), backend.stream()))
+            got = backend.download(d_buf)[:chunk]
+            assert np.array_equal(got, want[first:first + chunk]), (trial, qubits, values, first)
+        # scatter new data into the same positions
+        fresh = rng.normal(size=block) + 1j * rng.normal(size=block)
+        expect = shard.copy()
+        expect[sel] = fresh
+        for first in range(0, block, chunk):
+            d_part = backend.upload(fresh[first:first + chunk])
+            _capi.check(lib, lib.qsim_swap_unpack(backend.ptr(d_shard), backend.ptr(d_part), n, k, cq, cv,
+                                                  C.c_uint64(first), C.c_uint64(chunk), backend.stream()))
+        assert np.array_equal(backend.download(d_shard), expect)
+    # argument checks
+    d = backend.upload(np.zeros(8, dtype=np.complex128))
+    two = (C.c_int * 2)(1, 1)
+    assert lib.qsim_swap_pack(backend.ptr(d), backend.ptr(d), 3, 2, two, two, C.c_uint64(0), C.c_uint64(1),
+                              backend.stream()) != 0             # repeated qubit
+
+
 def check_plan_cache(backend):
     """Simulator keeps compiled plans between runs, keyed by the content of the segment:
     a second run must not plan again, and a gate mutated in between must be noticed."""
