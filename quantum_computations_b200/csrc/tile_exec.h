@@ -281,7 +281,14 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   const uint32_t slo = qs_swz(jlo);
   char* const t0 = reinterpret_cast<char*>(tile);
 
-  for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthr) {
+  // uniform trip count (a tile smaller than the CTA leaves the upper threads idle), so that
+  // loop-invariant uniform loads can be hoisted
+  uint32_t niter = nwork >> nthr_log2;
+  if (niter == 0) {
+    if (tid >= nwork) return;
+    niter = 1;
+  }
+  for (uint32_t i = 0; i < niter; ++i) {
     const uint32_t hi = tab.hi[i];
     const uint32_t j0 = jlo | (hi & 0xffffu);
     const uint32_t s0b = (slo ^ (hi >> 16)) << 4;
