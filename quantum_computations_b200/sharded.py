@@ -368,6 +368,23 @@ class ShardedSimulator:
         return local_bits, np.diag(sub)
 
     defer_tails = True      # leave each stage's trailing single-qubit phases to the next stage's plan
+    dense_caps = (18, 20, 22, 24)   # matrices-per-pass caps tried for every stage (0 entries: planner default)
+
+    def _best_plan(self, nloc, segment, options):
+        """A stage is a short circuit, and its last pass is often nearly empty; planning costs
+        tens of milliseconds, so try a few caps on the matrices per pass and keep the cheapest
+        plan under the measured cost model of DESIGN.md section 5 (4.1 ms per pass + 1.42 ms per
+        shared-memory round trip, per 2^30 amplitudes).  Ranks may decide differently (their
+        restricted diagonals differ) -- which is fine, plans are local."""
+        if options.get("max_dense_ops") or not self.dense_caps:
+            return engine.Plan(self.state.backend, nloc, segment, options)
+        best = None
+        for cap in self.dense_caps:
+            plan = engine.Plan(self.state.backend, nloc, segment, dict(options, max_dense_ops=cap))
+            key = 4.1 * plan.stats["n_passes"] + 1.42 * plan.stats["n_steps"]
+            if best is None or key < best[0]:
+                best = (key, plan)
+        return best[1]
 
     def _carry_controlled(self, out, leaving, l, mats):
         """The general case: a single-qubit gate on ``l`` selected by the ``leaving`` qubits."""
@@ -538,7 +555,7 @@ class ShardedSimulator:
                 if want_residual:
                     options["defer_tail"] = 1
                     options["apply_tail_mask"] = sum(1 << (nloc - 1 - lp) for _gp, lp in pairs)
-                plan = engine.Plan(st.backend, nloc, segment, options)
+                plan = self._best_plan(nloc, segment, options)
                 schedule.append(("plan", plan))
                 self.stats["segments"] += 1
                 self.stats["passes"] += plan.stats["n_passes"]
