@@ -161,12 +161,13 @@ int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int nbits, con
 int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, const int* local_qubits,
                      const int* bit_values, uint64_t first, uint64_t count, void* stream);
 
-/* ---- peer-to-peer staging for the swaps (one process per GPU) -----------------------
- * The travelling half shard moves with the copy engines, not with SM kernels: every
- * rank packs a chunk into a library-allocated staging buffer, exports it once through
- * CUDA IPC, and the partner PULLS it over NVLink with cudaMemcpyAsync while both GPUs'
- * SMs keep gathering / scattering the neighbouring chunks.  Ordering between the two
- * processes is the caller's (a stream-ordered token exchange, see sharded.py). */
+/* ---- peer-to-peer staging for the exchanges (one process per GPU) --------------------
+ * The travelling blocks move with the copy engines, not with SM kernels: every rank packs
+ * a chunk into a library-allocated staging buffer, exports its RECEIVE staging once through
+ * CUDA IPC, and PUSHES each packed chunk into the partner's receive staging over NVLink
+ * with cudaMemcpyAsync (writes are the fast direction of NVLink P2P) while both GPUs' SMs
+ * keep gathering / scattering the neighbouring chunks.  Ordering between the two
+ * processes is the caller's (stream-ordered token exchanges, see sharded.py). */
 int qsim_peer_alloc(int device, uint64_t bytes, void** out_ptr);       /* cudaMalloc                      */
 int qsim_peer_free(void* ptr);
 int qsim_ipc_export(void* ptr, unsigned char* handle64);               /* 64-byte cudaIpcMemHandle_t      */
