@@ -452,4 +452,20 @@ int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
   return QSIM_OK;
 }
 
+// Test-only: per pass (steps, matrices, sign pairs) -> out[3 * pass + {0,1,2}]; returns passes.
+int qsim_emu_plan_shape(const qsim_plan_t* p, int* out, int max_passes) {
+  if (!p || !out) return -1;
+  int k = 0;
+  for (const qs::PlanItem& it : p->items) {
+    if (it.generic || k >= max_passes) continue;
+    int mats = 0;
+    for (uint32_t s = 0; s < it.pass.nsteps; ++s) mats += it.pass.steps[s].kind == QS_STEP_1Q ? it.pass.steps[s].r : 1;
+    out[3 * k] = (int)it.pass.nsteps;
+    out[3 * k + 1] = mats;
+    out[3 * k + 2] = (int)it.pass.npairs;
+    ++k;
+  }
+  return k;
+}
+
 }  // extern "C"

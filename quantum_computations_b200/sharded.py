@@ -342,6 +342,9 @@ class ShardedSimulator:
         n = self.state.n
         out = []
         for gate in self.circuit:
+            if getattr(gate, "matrix", None) is None or not hasattr(gate, "lowered"):
+                raise NotImplementedError(f"ShardedSimulator runs matrix gates only (no measurement, insertion or "
+                                          f"classical control yet); got {gate!r}")
             for targets, matrix in gate.lowered(n, False):
                 m = np.asarray(matrix, dtype=np.complex128)
                 bits = [n - 1 - q for q in targets]

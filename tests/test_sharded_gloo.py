@@ -160,3 +160,15 @@ def test_leftovers_cross_an_exchange(tmp_path, world, n):
     assert err < 1e-12
     assert abs(nrm - ref_norm) < 1e-12
     assert signs > 0 and controlled > 0                 # (the scalar-only case is covered by the random circuits)
+
+
+def test_sharded_simulator_refuses_non_matrix_gates(emu_backend):
+    import types
+    from quantum_computations_b200 import gates, sharded
+    state = types.SimpleNamespace(n=5, g=1, n_local=4, backend=emu_backend, phys=list(range(5)), flip=[0],
+                                  comm=types.SimpleNamespace(rank=0, size=2))
+    with pytest.raises(NotImplementedError):
+        sharded.ShardedSimulator([gates.H(0), gates.MZ(1)], state).compile()
+    sim = sharded.ShardedSimulator([gates.H(0), gates.CZ(0, 4), gates.X(2)], state)
+    assert [kind for kind, *_ in sim.compile()] == ["plan"]      # qubit 0 is made local by the initial layout
+    assert sim.initial_phys != list(range(5)) and sim.stats["swaps"] == 0
