@@ -32,6 +32,7 @@ is fixed and everything runs on the shard through the single-GPU fused planner:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -146,7 +147,6 @@ class ShardedState:
     def _peer_setup(self, chunk: int):
         """Allocate the four staging chunks with the library (plain cudaMalloc, so they can be
         exported through CUDA IPC) and open every other rank's receive chunks once."""
-        import os
         be, lib = self.backend, self.backend.lib
         if self._peer is not None and self._peer["chunk"] == chunk:
             return self._peer
