@@ -285,6 +285,85 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
     return worst
 
 
+def check_edge_cases(backend):
+    """The corners: empty and diagonal-only circuits, registers of one qubit, gates on the
+    whole register, gates wider than a step (out-of-place generic kernel, k = 5 .. 7),
+    cancelling CZ pairs, reversed / scattered targets, empty and zero-length RB batches."""
+    rng = np.random.default_rng(99)
+
+    def rand_state(n):
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        return psi / np.linalg.norm(psi)
+
+    def rand_unitary(k):
+        return np.linalg.qr(rng.normal(size=(2 ** k, 2 ** k)) + 1j * rng.normal(size=(2 ** k, 2 ** k)))[0]
+
+    def run_both(circ, psi, **opts):
+        got = Simulator(circ, backend=backend, plan_options=opts or None).run(psi)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        return got, ref
+
+    # empty circuit: a copy of the input, not the input itself
+    psi = rand_state(5)
+    out = Simulator([], backend=backend).run(psi)
+    assert out is not psi and np.array_equal(out, psi)
+    assert np.array_equal(Simulator([], backend=backend).run([State.ZERO, State.ONE]), np.array([0, 1, 0, 0]))
+
+    # one qubit: gate, then the measurement that leaves a 0-d array (reference quirk)
+    one = Simulator([gates.H(0)], backend=backend).run(np.array([1.0, 0.0]))
+    assert rel_err(one, np.array([1.0, 1.0]) / np.sqrt(2)) < RTOL
+    np.random.seed(5)
+    sim = Simulator([gates.H(0), gates.MZ(0)], backend=backend)
+    left = sim.run(np.array([1.0, 0.0]))
+    assert np.shape(left) == () and sim.results[0] in (0, 1) and abs(abs(left) - 1.0) < 1e-12
+
+    # diagonal gates only (no matrix step at all), with CZ pairs that cancel and Z Z = 1
+    n = 7
+    psi = rand_state(n)
+    circ = [gates.T(0), gates.CZ(0, 6), gates.RZ(3, 0.7), gates.CZ(6, 0), gates.CZ(2, 5), gates.Z(4), gates.Z(4),
+            gates.P(6), gates.CZ(1, 2), gates.Tdg(2), gates.CZ(2, 5), gates.Pdg(1)]
+    got, ref = run_both(circ, psi, tile_bits=5, low_bits=2)
+    assert rel_err(got, ref) < RTOL
+
+    # a gate on the whole register, targets reversed and scattered
+    for n, idx in ((2, [1, 0]), (3, [2, 0, 1]), (4, [3, 1, 0, 2])):
+        psi = rand_state(n)
+        got, ref = run_both([gates.Gate(list(idx), rand_unitary(n))], psi)
+        assert rel_err(got, ref) < RTOL
+    psi = rand_state(9)
+    circ = [gates.Gate([7, 2], rand_unitary(2)), gates.Gate([8, 0, 4], rand_unitary(3)),
+            gates.Gate([5, 3, 6, 1], rand_unitary(4)), gates.H(8), gates.Gate([0, 8], rand_unitary(2))]
+    got, ref = run_both(circ, psi, tile_bits=6, low_bits=1)
+    assert rel_err(got, ref) < RTOL
+
+    # wider than a step: the out-of-place generic kernel, between fused segments
+    for k, n in ((5, 7), (6, 8), (7, 7)):
+        psi = rand_state(n)
+        idx = [int(q) for q in rng.permutation(n)[:k]]
+        circ = [gates.H(0), gates.CZ(0, n - 1), gates.Gate(idx, rand_unitary(k)), gates.T(idx[0]), gates.H(n - 1)]
+        got, ref = run_both(circ, psi)
+        assert rel_err(got, ref) < RTOL, (k, n)
+
+    # density matrix with a channel on a one-qubit register
+    rho = np.array([[0.75, 0.1 - 0.2j], [0.1 + 0.2j, 0.25]])
+    noise = channels.GKPNoise(9.0)
+    circ = noise.noisy([gates.H(0), gates.T(0)])
+    got = Simulator(circ, backend=backend).run(rho)
+    want = rho
+    for g in (gates.H(0), gates.T(0)):
+        want = dense_ref.apply_matrix(want, g.indices, g.matrix)
+        for q, (px, pz) in zip(g.indices, noise.flips_for(g)):
+            want = dense_ref.apply_kraus(want, [q], gkp_noise.pauli_flip_kraus(px, pz))
+    assert rel_err(got, want) < RTOL
+
+    # batched executor: nothing to do, and sequences without gates
+    empty = BatchedSimulator(2, None, backend=backend).run([])
+    assert empty["fidelity"].shape == (0,) and empty["purity"].shape == (0,)
+    idle = BatchedSimulator(2, channels.GKPNoise(10.0), backend=backend).run([[], [gates.H(0)], []])
+    assert np.allclose(idle["fidelity"][[0, 2]], 1.0, atol=1e-15) and np.allclose(idle["purity"][[0, 2]], 1.0, atol=1e-15)
+    assert idle["fidelity"][1] < 1.0
+
+
 def check_swap_pack_unpack(backend):
     """qsim_swap_pack / _unpack (the gather / scatter of a k-qubit exchange block) against
     NumPy indexing, chunked like the pipeline does."""

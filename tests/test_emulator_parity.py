@@ -54,6 +54,10 @@ def test_random_vs_oracle_default_tiles(emu_backend):
     pc.check_random_vs_oracle(emu_backend, trials=6, n_range=(12, 14), tile_range=(9, 12), seed=12)
 
 
+def test_edge_cases(emu_backend):
+    pc.check_edge_cases(emu_backend)
+
+
 def test_swap_pack_unpack(emu_backend):
     pc.check_swap_pack_unpack(emu_backend)
 

@@ -104,6 +104,10 @@ def test_tomography_of_a_noisy_gate(cuda_backend):
         assert np.abs(tomo.superoperator(fitted) - want).max() < 1e-12
 
 
+def test_edge_cases(cuda_backend):
+    pc.check_edge_cases(cuda_backend)
+
+
 def test_swap_pack_unpack(cuda_backend):
     pc.check_swap_pack_unpack(cuda_backend)
 
