@@ -326,10 +326,17 @@ class ShardedSimulator:
     ``compile()`` builds the stage schedule; ``prepare(vectors)`` builds the product
     state in the layout the first stage wants; ``run()`` executes."""
 
-    def __init__(self, circuit, state: ShardedState, plan_options=None):
+    def __init__(self, circuit, state: ShardedState, plan_options=None, density: bool = False):
+        """``density``: the state is vec(rho) of an N = state.n / 2 qubit register (row qubits
+        first, column qubits after them, as everywhere in this package): unitaries act as
+        U on q and conj(U) on q + N, Kraus channels as one superoperator on (q, q + N), and
+        the sharding is the same -- the first row qubits are the rank qubits to begin with."""
         self.circuit = circuit
         self.state = state
         self.plan_options = plan_options
+        self.density = bool(density)
+        if self.density and state.n % 2:
+            raise ValueError("a vectorised density matrix has an even number of index bits")
         self.stats = {"segments": 0, "passes": 0, "swaps": 0, "local_gates": 0, "exchange_units": 0.0,
                       "relabels": 0, "carried_common": 0, "carried_signs": 0, "carried_controlled": 0}
         self._schedule = None
@@ -340,12 +347,14 @@ class ShardedSimulator:
     def _lower(self):
         """[(logical_bits (factor order), matrix, kind)]"""
         n = self.state.n
+        nq = n // 2 if self.density else n
         out = []
         for gate in self.circuit:
-            if getattr(gate, "matrix", None) is None or not hasattr(gate, "lowered"):
-                raise NotImplementedError(f"ShardedSimulator runs matrix gates only (no measurement, insertion or "
-                                          f"classical control yet); got {gate!r}")
-            for targets, matrix in gate.lowered(n, False):
+            fusable = getattr(gate, "_fusable", False) and hasattr(gate, "lowered")
+            if not fusable:
+                raise NotImplementedError(f"ShardedSimulator runs matrix gates and channels only (no measurement, "
+                                          f"insertion or classical control yet); got {gate!r}")
+            for targets, matrix in gate.lowered(nq, self.density):
                 m = np.asarray(matrix, dtype=np.complex128)
                 bits = [n - 1 - q for q in targets]
                 out.append((bits, m, _kind(bits, m)))
@@ -591,10 +600,14 @@ class ShardedSimulator:
         return schedule
 
     def prepare(self, vectors) -> ShardedState:
-        """Product state (qubit 0 first) in the layout the first stage runs in."""
+        """Product state (qubit 0 first) in the layout the first stage runs in; with
+        ``density`` the N kets give rho = |psi><psi|, i.e. vec(rho) = psi (x) conj(psi)."""
         if self._schedule is None:
             self.compile()
-        self.state.set_product(vectors, self.initial_phys)
+        vecs = [np.asarray(v, dtype=np.complex128) for v in vectors]
+        if self.density:
+            vecs = vecs + [np.conjugate(v) for v in vecs]
+        self.state.set_product(vecs, self.initial_phys)
         return self.state
 
     def run(self) -> ShardedState:

@@ -107,6 +107,59 @@ def test_sharded_matches_oracle(tmp_path, world, n):
     assert common > 0                                    # leftovers of a plan were carried across an exchange
 
 
+def _density_worker(rank, world, port, nq, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emu_backend import emu
+        from oracle import dense_ref, gkp_noise
+        from quantum_computations_b200 import channels, sharded, workloads
+        from quantum_computations_b200.states import State
+
+        comm = sharded.Comm()
+        noise = channels.GKPNoise(9.0)
+        layers = workloads.dm_random_layers(nq, 5, 21)
+        clean = [g for layer in layers for g in layer]
+        circ = noise.noisy(clean)                               # every gate followed by its Kraus channel(s)
+        kets = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (nq - 2)
+        st = sharded.ShardedState(2 * nq, comm, backend=emu(), as_torch=torch.from_numpy)
+        sharded.ShardedState.CHUNK_LOG2 = 4
+        sim = sharded.ShardedSimulator(circ, st, plan_options=dict(tile_bits=6, low_bits=2), density=True)
+        sim.prepare(kets)
+        sim.run()
+        got = st.gather_numpy().reshape(2 ** nq, 2 ** nq)
+        if rank == 0:
+            psi = np.ones(1)
+            for v in kets:
+                psi = np.kron(psi, v)
+            rho = np.outer(psi, np.conjugate(psi))
+            for g in clean:
+                rho = dense_ref.apply_matrix(rho, g.indices, g.matrix)
+                for q, (px, pz) in zip(g.indices, noise.flips_for(g)):
+                    rho = dense_ref.apply_kraus(rho, [q], gkp_noise.pauli_flip_kraus(px, pz))
+            err = float(np.abs(got - rho).max() / np.abs(rho).max())
+            np.save(os.path.join(out_dir, "density.npy"),
+                    np.array([err, abs(np.trace(got) - 1.0), sim.stats["swaps"], sim.stats["passes"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 4), (4, 5)])
+def test_sharded_density_matrix_matches_oracle(tmp_path, world, nq):
+    """SURVEY 8e, second row: a vectorised density matrix (2N index bits) sharded by its
+    first row qubits, with Kraus channels after every gate, against the oracle's
+    U rho U^dagger / sum K rho K^dagger path."""
+    port = _free_port()
+    mp.spawn(_density_worker, args=(world, port, nq, str(tmp_path)), nprocs=world, join=True)
+    err, trace_err, swaps, passes = np.load(tmp_path / "density.npy")
+    assert err < 1e-12 and trace_err < 1e-12
+    assert swaps > 0 and passes > 0
+
+
 def _exchange_worker(rank, world, port, n, out_dir):
     for p in (ROOT, HERE):
         if p not in sys.path:
