@@ -28,6 +28,9 @@ is fixed and everything runs on the shard through the single-GPU fused planner:
   travelling blocks; the transfer is a copy-engine push over NVLink (CUDA IPC) on
   GPUs and a send/recv elsewhere.  The first stage costs nothing: the initial product
   state is built directly in the layout the schedule wants.
+
+``ShardedSimulator.run_circuit`` adds measurements, insertions and classical control
+(``Simulator.run`` semantics); ``density=True`` shards a vectorised density matrix.
 """
 from __future__ import annotations
 
@@ -295,6 +298,84 @@ class ShardedState:
             la, lb = self.phys.index(gp), self.phys.index(lp)
             self.phys[la], self.phys[lb] = lp, gp
 
+    # -- measurement and insertion (DV/gates.py:145-186 on a sharded ket) ----------------------------
+    def _make_local(self, logical: int) -> bool:
+        """Bring a rank qubit into the shard (one single-qubit exchange with the top local bit).
+        Returns True when the qubit arrives complemented (its rank bit carried the flip flag;
+        the flag is cleared, the new occupant of the rank bit is stored as it is)."""
+        p = self.phys[logical]
+        if p < self.n_local:
+            return False
+        i = p - self.n_local
+        self.exchange([(p, self.n_local - 1)])
+        complemented = bool(self.flip[i])
+        self.flip[i] = 0
+        return complemented
+
+    def measure(self, qubit: int, vec0, vec1, forced=None) -> int:
+        """M.apply (DV/gates.py:165-186): contract reference qubit ``qubit`` with the
+        un-conjugated vectors, draw the outcome on rank 0 from NumPy's global legacy generator
+        (like the reference) and share it, collapse and renormalise.  The register loses the
+        qubit; every rank's shard halves."""
+        if self.n_local < 2:
+            raise ValueError("shards of a single amplitude cannot be measured; use fewer ranks")
+        if not 0 <= qubit < self.n:
+            raise ValueError("new_ordering must be a permutation of all qubits")
+        be, lib = self.backend, self.backend.lib
+        logical = self.n - 1 - qubit
+        complemented = self._make_local(logical)
+        p = self.phys[logical]                       # local now
+        vecs = [np.ascontiguousarray(np.asarray(vec0, dtype=np.complex128).reshape(2)),
+                np.ascontiguousarray(np.asarray(vec1, dtype=np.complex128).reshape(2))]
+        if complemented:                             # contracting a complemented bit = swapping the bra's entries
+            vecs = [v[::-1].copy() for v in vecs]
+        j = self.n_local - 1 - p
+        part = np.zeros(2)
+        _capi.check(lib, lib.qsim_measure_probs(be.ptr(self.buf), self.n_local, int(j),
+                                                vecs[0].view(np.float64).ctypes.data_as(_capi.c_double_p),
+                                                vecs[1].view(np.float64).ctypes.data_as(_capi.c_double_p),
+                                                part.ctypes.data_as(_capi.c_double_p), be.stream()))
+        probs = self.comm.allreduce_sum(part)
+        norm0, norm1 = np.sqrt(probs[0]), np.sqrt(probs[1])
+        pick = np.zeros(1)
+        if self.comm.rank == 0:
+            pick[0] = forced if forced is not None else int(np.random.choice([0, 1], p=[norm0 ** 2, norm1 ** 2]))
+        outcome = int(round(self.comm.allreduce_sum(pick)[0]))
+        out = be.empty(1 << (self.n_local - 1))
+        bra = vecs[outcome]
+        _capi.check(lib, lib.qsim_collapse(be.ptr(self.buf), be.ptr(out), self.n_local, int(j),
+                                           bra.view(np.float64).ctypes.data_as(_capi.c_double_p),
+                                           float((norm0, norm1)[outcome]), be.stream()))
+        self.buf = out
+        # the qubit is gone: logical bits above it and physical bits above its position move down
+        new_phys = []
+        for l, q in enumerate(self.phys):
+            if l == logical:
+                continue
+            new_phys.append(q - 1 if q > p else q)
+        self.phys = new_phys
+        self.n -= 1
+        self.n_local -= 1
+        return outcome
+
+    def insert(self, position: int, amp) -> None:
+        """Insert.apply (DV/gates.py:145-153): a new qubit in state ``amp`` at reference
+        position ``position``.  It becomes the top local bit of every shard, which doubles."""
+        if not 0 <= position <= self.n:
+            raise ValueError("new_ordering must be a permutation of all qubits")
+        be, lib = self.backend, self.backend.lib
+        v = np.ascontiguousarray(np.asarray(amp, dtype=np.complex128).reshape(2))
+        out = be.empty(1 << (self.n_local + 1))
+        _capi.check(lib, lib.qsim_insert(be.ptr(self.buf), be.ptr(out), self.n_local, 0,
+                                         v.view(np.float64).ctypes.data_as(_capi.c_double_p), be.stream()))
+        self.buf = out
+        new_logical = self.n - position                  # in the grown register
+        top = self.n_local                               # physical position of the new bit
+        grown = [q + 1 if q >= top else q for q in self.phys]
+        self.phys = grown[:new_logical] + [top] + grown[new_logical:]
+        self.n += 1
+        self.n_local += 1
+
     # -- gathering (tests / small registers only) -----------------------------------------------------
     def gather_numpy(self) -> np.ndarray:
         """Full state in logical order on every rank."""
@@ -493,9 +574,12 @@ class ShardedSimulator:
         order = sorted(range(n), key=lambda l: (-dist.get(l, 1 << 60), 0 if l in current else 1, -l))
         return set(order[:g])
 
-    def compile(self):
+    def compile(self, fixed_layout: bool = False):
         """Cut the circuit into stages (see the module docstring) and build one fused
-        local plan per stage, separated by multi-qubit exchanges."""
+        local plan per stage, separated by multi-qubit exchanges.  With ``fixed_layout`` the
+        schedule starts from the state's current layout and flip flags (a circuit that continues
+        on a live state); otherwise the first stage picks its own rank qubits and ``prepare``
+        builds the product state accordingly."""
         st = self.state
         ops = self._lower()
         n, g, nloc = st.n, st.g, st.n_local
@@ -503,15 +587,21 @@ class ShardedSimulator:
         schedule = []
 
         pending = list(range(len(ops)))
-        # stage 0: the product state can be built in any layout, so choose before moving anything
-        glob = self._choose_rank_qubits(ops, pending, set(), n, g)
-        phys = [0] * n
-        for i, l in enumerate(sorted(glob)):
-            phys[l] = nloc + i
-        for i, l in enumerate(l for l in range(n) if l not in glob):
-            phys[l] = i
+        if fixed_layout:
+            phys = list(st.phys)
+            glob = {l for l in range(n) if phys[l] >= nloc}
+            flip = list(st.flip)
+        else:
+            # stage 0: the product state can be built in any layout, so choose before moving anything
+            glob = self._choose_rank_qubits(ops, pending, set(), n, g)
+            phys = [0] * n
+            for i, l in enumerate(sorted(glob)):
+                phys[l] = nloc + i
+            for i, l in enumerate(l for l in range(n) if l not in glob):
+                phys[l] = i
+            flip = [0] * g
         self.initial_phys = list(phys)
-        flip = [0] * g
+        self.initial_flip = list(flip)
         carry = []                                   # [(logical bits, matrix)] to run before anything else
 
         while True:
@@ -599,6 +689,55 @@ class ShardedSimulator:
         self._schedule = schedule
         return schedule
 
+    def run_circuit(self, vectors) -> ShardedState:
+        """``Simulator.run`` semantics (DV/simulator.py:36-53) on a sharded ket, for circuits
+        that also measure, insert qubits and feed results forward: maximal runs of matrix
+        gates go through the stage scheduler (the first one picks the layout the product state
+        is built in, the later ones continue from the live layout), ``M`` / ``Insert`` /
+        ``ClassicalControl`` act in between.  Outcomes end up in ``self.results``."""
+        from .gates import Insert, M
+        from .simulator import ClassicalControl
+        if self.density:
+            raise NotImplementedError("measurements on a sharded density matrix are not defined (SURVEY 3.3)")
+        st = self.state
+        vecs = [np.asarray(v, dtype=np.complex128) for v in vectors]
+        self.results = []
+        segment, prepared = [], False
+
+        def flush():
+            nonlocal prepared
+            sub = None
+            if segment:
+                sub = ShardedSimulator(list(segment), st, self.plan_options)
+                sub.compile(fixed_layout=prepared)
+            if not prepared:
+                st.set_product(vecs, sub.initial_phys if sub else None)
+                prepared = True
+            if sub:
+                sub.run()
+                for key, val in sub.stats.items():
+                    self.stats[key] = self.stats.get(key, 0) + val
+            segment.clear()
+
+        for gate in self.circuit:
+            if isinstance(gate, ClassicalControl):
+                if not gate.eval(self.results):          # every M before it has run: it ended a segment
+                    continue
+                gate = gate.gate
+            if isinstance(gate, M):
+                flush()
+                v0, v1 = gate.vectors()
+                self.results.append(st.measure(gate.indices[0], v0, v1, gate.result))
+            elif isinstance(gate, Insert):
+                flush()
+                st.insert(gate.indices[0], gate.state.get())
+            elif getattr(gate, "_fusable", False):
+                segment.append(gate)
+            else:
+                raise NotImplementedError(f"ShardedSimulator cannot run {gate!r}")
+        flush()
+        return st
+
     def prepare(self, vectors) -> ShardedState:
         """Product state (qubit 0 first) in the layout the first stage runs in; with
         ``density`` the N kets give rho = |psi><psi|, i.e. vec(rho) = psi (x) conj(psi)."""
@@ -616,7 +755,7 @@ class ShardedSimulator:
         st = self.state
         if self._schedule is None:
             self.compile()
-        if st.phys != self.initial_phys or any(st.flip):
+        if st.phys != self.initial_phys or list(st.flip) != list(getattr(self, "initial_flip", [0] * st.g)):
             raise ValueError("the state is not in the schedule's initial layout; call prepare() first")
         for item in self._schedule:
             if item[0] == "plan":

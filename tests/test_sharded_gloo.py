@@ -160,6 +160,76 @@ def test_sharded_density_matrix_matches_oracle(tmp_path, world, nq):
     assert swaps > 0 and passes > 0
 
 
+def _feedforward_circuit(gates, workloads, ClassicalControl, State, n):
+    """Measurements of rank and local qubits, a qubit insertion, feed-forward, and random
+    layers in between so that exchanges happen on the live layout."""
+    circ = [gates.H(0), gates.CX(0, 1), gates.H(2), gates.CZ(2, 3), gates.T(3)]
+    circ += workloads.sv_random_circuit(n, 3, 5)
+    circ += [gates.MZ(0),                                     # reference qubit 0 starts as a rank qubit
+             ClassicalControl(gates.X(0), [0]),               # (qubit numbers shift after a measurement)
+             gates.Insert(2, State.PLUS), gates.H(3)]
+    circ += workloads.sv_random_circuit(n, 2, 6)
+    circ += [gates.MX(n - 1), ClassicalControl(gates.Z(1), [], [1]), gates.M(4, 0.3, 1.1)]
+    circ += workloads.sv_random_circuit(n - 2, 3, 7)
+    circ += [gates.Insert(0, State.T), gates.MZ(1), ClassicalControl(gates.H(0), [-1])]
+    return circ
+
+
+def _feedforward_worker(rank, world, port, n, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emu_backend import emu
+        from quantum_computations_b200 import gates, sharded, workloads
+        from quantum_computations_b200.simulator import ClassicalControl, Simulator
+        from quantum_computations_b200.states import State
+
+        be = emu()
+        comm = sharded.Comm()
+        circ = _feedforward_circuit(gates, workloads, ClassicalControl, State, n)
+        kets = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (n - 2)
+        worst, all_results = 0.0, []
+        for seed in (1, 2, 3):
+            st = sharded.ShardedState(n, comm, backend=be, as_torch=torch.from_numpy)
+            sharded.ShardedState.CHUNK_LOG2 = 4
+            sim = sharded.ShardedSimulator(circ, st, plan_options=dict(tile_bits=5, low_bits=1))
+            np.random.seed(seed)                               # only rank 0 draws
+            sim.run_circuit(kets)
+            got = st.gather_numpy()
+            if rank == 0:
+                psi0 = np.ones(1)
+                for v in kets:
+                    psi0 = np.kron(psi0, v)
+                np.random.seed(seed)
+                single = Simulator(circ, backend=be)
+                ref = single.run(psi0.astype(np.complex128))
+                assert sim.results == single.results, (sim.results, single.results)
+                assert got.shape == ref.shape
+                worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+                all_results.append(tuple(sim.results))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "feedforward.npy"),
+                    np.array([worst, len(set(all_results)), sim.stats["swaps"], st.n]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 8), (4, 9)])
+def test_sharded_measurement_insertion_feedforward(tmp_path, world, n):
+    """Simulator.run semantics on a sharded ket: M on rank and local qubits (same outcome
+    stream as the single-process simulator from the same seed), Insert, ClassicalControl."""
+    port = _free_port()
+    mp.spawn(_feedforward_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    worst, distinct, swaps, n_final = np.load(tmp_path / "feedforward.npy")
+    assert worst < 1e-12
+    assert n_final == n - 2                              # four measurements, two insertions
+    assert distinct >= 2                                 # the seeds did not all give the same outcomes
+
+
 def _exchange_worker(rank, world, port, n, out_dir):
     for p in (ROOT, HERE):
         if p not in sys.path:
