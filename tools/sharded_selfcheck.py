@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--qubits", type=int, default=0)
     ap.add_argument("--depth", type=int, default=60)
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--feedforward", action="store_true",
+                    help="(<= 28 qubits) a circuit with measurements, insertions and classical control through "
+                         "run_circuit, against the single-GPU Simulator from the same seed")
     ap.add_argument("--compare-single", action="store_true",
                     help="(<= 28 qubits) run the forward circuit only and compare the gathered state element by "
                          "element with the single-GPU Simulator on rank 0")
@@ -42,6 +45,36 @@ def main():
     comm = sharded.Comm()
     comm.device = torch.device("cuda", local)
     forward = workloads.sv_random_circuit(n, args.depth, args.seed)
+    if args.feedforward:
+        from quantum_computations_b200 import gates
+        from quantum_computations_b200.simulator import ClassicalControl, Simulator
+        circ = [gates.H(0), gates.CX(0, 1), gates.H(2), gates.CZ(2, 3), gates.T(3)]
+        circ += workloads.sv_random_circuit(n, 6, 5)
+        circ += [gates.MZ(0), ClassicalControl(gates.X(0), [0]), gates.Insert(2, State.PLUS), gates.H(3)]
+        circ += workloads.sv_random_circuit(n, 6, 6)
+        circ += [gates.MX(n - 1), ClassicalControl(gates.Z(1), [], [1]), gates.M(4, 0.3, 1.1)]
+        circ += workloads.sv_random_circuit(n - 2, 6, 7)
+        circ += [gates.Insert(0, State.T), gates.MZ(1), ClassicalControl(gates.H(0), [-1])]
+        kets = [State.PLUS.get(), State.T.get()] + [State.ZERO.get()] * (n - 2)
+        state = sharded.ShardedState(n, comm, backend=backend)
+        sim = sharded.ShardedSimulator(circ, state)
+        np.random.seed(args.seed)
+        sim.run_circuit(kets)
+        got = state.gather_numpy()
+        if rank == 0:
+            psi0 = np.ones(1, dtype=np.complex128)
+            for k in kets:
+                psi0 = np.kron(psi0, np.asarray(k, dtype=np.complex128))
+            np.random.seed(args.seed)
+            single = Simulator(circ, backend=backend)
+            ref = single.run(psi0)
+            err = float(np.abs(got - ref).max() / np.abs(ref).max())
+            print(json.dumps({"check": "run_circuit (M, Insert, ClassicalControl) sharded vs single-GPU", "qubits": n,
+                              "gpus": world, "gates": len(circ), "results": sim.results,
+                              "same_outcomes": sim.results == single.results, "max_rel_err": err,
+                              "exchanges": state.swaps, "ok": bool(err < 1e-12 and sim.results == single.results)}))
+        dist.destroy_process_group()
+        return
     if args.compare_single:
         if n > 28:
             raise SystemExit("--compare-single gathers the state on the host: at most 28 qubits")
