@@ -109,95 +109,58 @@ class Gate:
 
 class SingleQubitGate(Gate):
     def __init__(self, index: int, matrix):
-        super().__init__([index], matrix)
+        Gate.__init__(self, [index], matrix)
 
 
 class TwoQubitGate(Gate):
     def __init__(self, index1: int, index2: int, matrix):
-        super().__init__([index1, index2], matrix)
+        Gate.__init__(self, [index1, index2], matrix)
 
 
-# ---- fixed-matrix gates (gates.py:67-85, :116-134) ------------------------------------------
-class I(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, npq.IDTY)
-
-
-class X(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, npq.X)
-
-
-class Y(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, npq.Y)
-
-
-class Z(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, npq.Z)
-
-
-class H(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, npq.H)
-
-
-# ---- z rotations: diag(e^{-i a/2}, e^{+i a/2}) (gates.py:87-114) -----------------------------
-def _rz(angle: float) -> np.ndarray:
+# ---- the fixed-matrix zoo (gates.py:67-134), generated from a table ---------------------------
+# Every entry becomes a class of that name whose constructor takes the qubit index (or the
+# two indices) and nothing else, as in the reference; GKP/ dispatches on these types by name.
+def _z_rotation(angle: float) -> np.ndarray:
+    """diag(e^{-i a/2}, e^{+i a/2}): RZ, and P / Pdg / T / Tdg as its quarter and eighth turns."""
     return npq.axis_rotation(angle, [0, 0, 1])
+
+
+def _one_qubit_class(name: str, build):
+    def __init__(self, index):
+        SingleQubitGate.__init__(self, index, build())
+    return type(name, (SingleQubitGate,), {"__init__": __init__, "__module__": __name__, "__qualname__": name})
+
+
+def _two_qubit_class(name: str, build, first: str, second: str, extras=None):
+    # the argument names are part of the surface (keyword calls): built with exec to keep them
+    namespace = {"TwoQubitGate": TwoQubitGate, "_build": build}
+    exec(f"def __init__(self, {first}, {second}):\n    TwoQubitGate.__init__(self, {first}, {second}, _build())", namespace)
+    body = {"__init__": namespace["__init__"], "__module__": __name__, "__qualname__": name}
+    body.update(extras or {})
+    return type(name, (TwoQubitGate,), body)
+
+
+_ONE_QUBIT_TABLE = {
+    "I": lambda: npq.IDTY, "X": lambda: npq.X, "Y": lambda: npq.Y, "Z": lambda: npq.Z, "H": lambda: npq.H,
+    "P": lambda: _z_rotation(np.pi / 2), "Pdg": lambda: _z_rotation(-np.pi / 2),
+    "T": lambda: _z_rotation(np.pi / 4), "Tdg": lambda: _z_rotation(-np.pi / 4),
+}
+I, X, Y, Z, H, P, Pdg, T, Tdg = (_one_qubit_class(_name, _build) for _name, _build in _ONE_QUBIT_TABLE.items())
+
+CX = _two_qubit_class("CX", lambda: npq.CX, "control", "target",
+                      {"control": property(lambda self: self.indices[0]),
+                       "target": property(lambda self: self.indices[1])})
+CZ = _two_qubit_class("CZ", lambda: npq.CZ, "index1", "index2")
+SWAP = _two_qubit_class("SWAP", lambda: npq.SWAP, "index1", "index2")
 
 
 class RZ(SingleQubitGate):
     def __init__(self, index, angle: float):
-        super().__init__(index, _rz(angle))
+        SingleQubitGate.__init__(self, index, _z_rotation(angle))
         self.angle = angle
 
     def __repr__(self):
-        return super().__repr__() + f"({round(self.angle, REPR_DIGITS)})"
-
-
-class P(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, _rz(np.pi / 2))
-
-
-class Pdg(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, _rz(-np.pi / 2))
-
-
-class T(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, _rz(np.pi / 4))
-
-
-class Tdg(SingleQubitGate):
-    def __init__(self, index):
-        super().__init__(index, _rz(-np.pi / 4))
-
-
-class CX(TwoQubitGate):
-    def __init__(self, control, target):
-        super().__init__(control, target, npq.CX)
-
-    @property
-    def control(self):
-        return self.indices[0]
-
-    @property
-    def target(self):
-        return self.indices[1]
-
-
-class CZ(TwoQubitGate):
-    def __init__(self, index1, index2):
-        super().__init__(index1, index2, npq.CZ)
-
-
-class SWAP(TwoQubitGate):
-    def __init__(self, index1, index2):
-        super().__init__(index1, index2, npq.SWAP)
+        return f"{Gate.__repr__(self)}({round(self.angle, REPR_DIGITS)})"
 
 
 # ---- register-resizing operations (gates.py:136-194) ------------------------------------------
@@ -205,11 +168,11 @@ class Insert(SingleQubitGate):
     """Grow the register by one qubit, prepared in ``state``, at position ``index``."""
 
     def __init__(self, index: int, state: State):
-        super().__init__(index, state.get().reshape((1, 2)))
+        SingleQubitGate.__init__(self, index, state.get().reshape((1, 2)))
         self.state = state
 
     def __repr__(self):
-        return super().__repr__() + f"({self.state})"
+        return f"{Gate.__repr__(self)}({self.state})"
 
     def apply(self, state):
         from . import engine
@@ -228,7 +191,7 @@ class M(SingleQubitGate):
     generator, both exactly as in the reference (gates.py:169-183)."""
 
     def __init__(self, index: int, theta: float, phi: float, *, result: int = None):
-        super().__init__(index, None)
+        SingleQubitGate.__init__(self, index, None)
         if result is not None and result not in [0, 1]:
             raise ValueError(f"Measurement results must be from 0 or 1 but {result} was given.")
         self.theta = theta
@@ -252,9 +215,9 @@ class M(SingleQubitGate):
 
 class MZ(M):
     def __init__(self, index, *, result=None):
-        super().__init__(index, 0.0, 0.0, result=result)
+        M.__init__(self, index, 0.0, 0.0, result=result)
 
 
 class MX(M):
     def __init__(self, index, *, result=None):
-        super().__init__(index, np.pi / 2, 0.0, result=result)
+        M.__init__(self, index, np.pi / 2, 0.0, result=result)

@@ -18,29 +18,32 @@ from __future__ import annotations
 import numpy as np
 
 # ---- constants (numpy_quantum.py:5-25) --------------------------------------
+# Integer where the reference is integer, float where it is float, complex where complex:
+# result dtypes follow NumPy promotion, so the element types are part of the interface.
 _RT2 = np.sqrt(2)
+_ket = lambda a, b, scale=1: np.array([a, b]) / scale if scale != 1 else np.array([a, b])   # noqa: E731
 
-ZERO = np.array([1, 0])
-ONE = np.array([0, 1])
-PLUS = np.array([1, 1]) / _RT2
-MINUS = np.array([1, -1]) / _RT2
-IPLUS = np.array([1, 1j]) / _RT2
-IMINUS = np.array([1, -1j]) / _RT2
+ZERO, ONE = _ket(1, 0), _ket(0, 1)
+PLUS, MINUS = _ket(1, 1, _RT2), _ket(1, -1, _RT2)
+IPLUS, IMINUS = _ket(1, 1j, _RT2), _ket(1, -1j, _RT2)
 
 IDTY = np.identity(2)
-X = np.array([[0, 1], [1, 0]])
-Y = np.array([[0, -1j], [1j, 0]])
-Z = np.array([[1, 0], [0, -1]])
+X = np.array([[0, 1],
+              [1, 0]])
+Y = np.array([[0, -1j],
+              [1j, 0]])
+Z = np.array([[1, 0],
+              [0, -1]])
 PAULIS = [X, Y, Z]
+H = (X + Z) / _RT2
 
-H = np.array([[1, 1], [1, -1]]) / _RT2
-
+_EYE4 = np.identity(4)
 CZ = np.diag([1.0, 1.0, 1.0, -1.0])
-CX = np.identity(4)[[0, 1, 3, 2]]
-SWAP = np.identity(4)[[0, 2, 1, 3]]
+CX = _EYE4[[0, 1, 3, 2]]          # permutation matrices, float64 like the reference's
+SWAP = _EYE4[[0, 2, 1, 3]]
 
-P = np.array([[1.0, 0.0], [0.0, 1.0j]])
-T = np.array([[1.0, 0.0], [0.0, np.exp(0.25j * np.pi)]])
+P = np.diag([1.0, 1.0j])
+T = np.diag([1.0, np.exp(0.25j * np.pi)])
 
 
 # ---- Pauli bookkeeping (numpy_quantum.py:28-76) ------------------------------
@@ -53,7 +56,7 @@ _PAULI_BY_AXIS = {(1, 0, 0): 1, (0, 1, 0): 2, (0, 0, 1): 3,
                   (-1, 0, 0): -1, (0, -1, 0): -2, (0, 0, -1): -3}
 
 
-def get_pauli_number(pauli_identifier) -> int:
+def get_pauli_number(pauli_identifier):
     """0 = I, 1..3 = X, Y, Z, negative = the negated operator.  Accepts names
     ('x', 'X', '-z', ...), the numbers themselves, or a unit axis [a, b, c]."""
     found = None
@@ -76,21 +79,23 @@ def get_pauli_number(pauli_identifier) -> int:
     return found
 
 
-def get_pauli_identifier(pauli_identifier) -> str:
+def get_pauli_identifier(pauli_identifier):
     names = {-3: "-Z", -2: "-Y", -1: "-X", 0: "I", 1: "X", 2: "Y", 3: "Z"}
     return names[get_pauli_number(pauli_identifier)]
 
 
-def is_pauli(case) -> bool:
+def is_pauli(case):
+    """Whether ``case`` names a (possibly negated) Pauli operator or the identity."""
     try:
         get_pauli_number(case)
+        return True
     except PauliError:
         return False
-    return True
 
 
-def get_pauli_operator(pauli_identifier) -> np.ndarray:
-    return PAULIS[get_pauli_number(pauli_identifier) - 1]
+def get_pauli_operator(pauli_identifier):
+    number = get_pauli_number(pauli_identifier)
+    return PAULIS[number - 1]
 
 
 def get_pauli_states(pauli_identifier):
@@ -98,8 +103,9 @@ def get_pauli_states(pauli_identifier):
     return eigenbases[get_pauli_number(pauli_identifier) - 1]
 
 
-def get_pauli_state(pauli_identifier, state_index: int) -> np.ndarray:
-    return get_pauli_states(pauli_identifier)[state_index]
+def get_pauli_state(pauli_identifier, state_index):
+    basis = get_pauli_states(pauli_identifier)
+    return basis[state_index]
 
 
 # ---- state builders (numpy_quantum.py:79-101) ---------------------------------
@@ -119,34 +125,41 @@ def basis_state(identifier, N: int | None = None) -> np.ndarray:
 
 
 def qubit_from_polar(theta: float, phi: float) -> np.ndarray:
-    return np.cos(theta / 2) * ZERO + np.exp(1j * phi) * np.sin(theta / 2) * ONE
+    half = theta / 2
+    return np.array([np.cos(half), np.exp(1j * phi) * np.sin(half)])
 
 
 def qubit_from_axis(axis) -> np.ndarray:
-    length = np.sqrt(sum(a ** 2 for a in axis))
-    return qubit_from_polar(np.arccos(axis[-1] / length), np.arctan2(axis[1], axis[0]))
+    ax, ay, az = axis[0], axis[1], axis[-1]
+    polar = np.arccos(az / np.sqrt(sum(a ** 2 for a in axis)))
+    return qubit_from_polar(polar, np.arctan2(ay, ax))
 
 
 # ---- small-matrix builders (numpy_quantum.py:100-109, :250-251) ---------------
-def phase_gate(theta: float) -> np.ndarray:
-    return np.array([[1, 0], [0, np.exp(1j * theta)]])
+def phase_gate(theta):
+    return np.diag([1, np.exp(1j * theta)])
 
 
 def axis_rotation(theta: float, axis) -> np.ndarray:
     """exp(-i theta/2 n.sigma).  The DV gate classes RZ/P/Pdg/T/Tdg are built
     from this, *not* from the constants ``P``/``T`` above (global phase)."""
-    generator = axis[0] * X + axis[1] * Y + axis[2] * Z
-    return IDTY * np.cos(theta / 2) - 1j * generator * np.sin(theta / 2)
+    n_sigma = sum(component * pauli for component, pauli in zip(axis, PAULIS))
+    half = theta / 2
+    return np.cos(half) * IDTY - 1j * np.sin(half) * n_sigma
 
 
-def euler_rotation(theta1, theta2, theta3) -> np.ndarray:
+def euler_rotation(theta1, theta2, theta3):
     rx = lambda t: axis_rotation(t, [1, 0, 0])
     return rx(theta3) @ axis_rotation(theta2, [0, 0, 1]) @ rx(theta1)
 
 
-def add_control(gate: np.ndarray) -> np.ndarray:
+def add_control(gate):
+    """|0><0| (x) 1 + |1><1| (x) gate."""
     dim = gate.shape[0]
-    return tensor(np.outer(ZERO, ZERO), np.identity(dim)) + tensor(np.outer(ONE, ONE), gate)
+    out = np.zeros((2 * dim, 2 * dim), dtype=np.result_type(gate.dtype, np.float64))
+    out[:dim, :dim] = np.identity(dim)
+    out[dim:, dim:] = gate
+    return out
 
 
 # ---- ket / density-matrix helpers (numpy_quantum.py:112-166) -------------------
@@ -154,10 +167,10 @@ def _is_device(obj) -> bool:
     return hasattr(obj, "_qsim_device_state")
 
 
-def ket2dm(ket: np.ndarray) -> np.ndarray:
-    if len(ket.shape) != 1:
+def ket2dm(ket):
+    if ket.ndim != 1:
         raise TypeError("state is not a ket")
-    return np.outer(ket, np.conjugate(ket))
+    return ket[:, None] * np.conjugate(ket)[None, :]
 
 
 def dm2ket(dm: np.ndarray, strict: bool = True) -> np.ndarray:
@@ -172,19 +185,21 @@ def dm2ket(dm: np.ndarray, strict: bool = True) -> np.ndarray:
 def norm(ket) -> float:
     if _is_device(ket):
         return ket.norm()
-    return np.linalg.norm(ket)
+    return np.linalg.norm(np.asarray(ket))
 
 
-def normalise(state: np.ndarray) -> np.ndarray:
-    if state.ndim == 1:
-        return state / np.linalg.norm(state)
-    if state.ndim == 2:
-        return state / np.trace(state)
-    raise ValueError("State not ket nor density matrix.")
+def normalise(state):
+    """Unit 2-norm for kets, unit trace for density matrices."""
+    scale = {1: np.linalg.norm, 2: np.trace}.get(state.ndim)
+    if scale is None:
+        raise ValueError("State not ket nor density matrix.")
+    return state / scale(state)
 
 
-def compare_kets(a: np.ndarray, b: np.ndarray) -> bool:
-    return np.allclose(ket2dm(normalise(a)), ket2dm(normalise(b)))
+def compare_kets(a, b):
+    """Equality up to a global phase (and normalisation)."""
+    rho_a, rho_b = (ket2dm(normalise(k)) for k in (a, b))
+    return np.allclose(rho_a, rho_b)
 
 
 def fidelity(a, b) -> float:
@@ -198,9 +213,9 @@ def fidelity(a, b) -> float:
     if a_ket and b_ket:
         return np.abs(a.conj() @ b).real ** 2
     if a_ket:
-        return (a.conj() @ b @ a).real
+        return np.vdot(a, b @ a).real
     if b_ket:
-        return (b.conj() @ a @ b).real
+        return np.vdot(b, a @ b).real
     spectrum = np.clip(np.linalg.eigvals(a @ b).real, 0.0, None)
     return np.sum(np.sqrt(spectrum)) ** 2
 
@@ -208,57 +223,61 @@ def fidelity(a, b) -> float:
 def purity(rho) -> float:
     if _is_device(rho):
         return rho.purity()
-    return np.trace(rho @ rho).real
+    return np.einsum("ij,ji->", rho, rho).real
 
 
 # ---- tensor-product plumbing (numpy_quantum.py:169-258) ------------------------
-def tensor(*arrays) -> np.ndarray:
+def tensor(*arrays):
     out = 1
     for factor in arrays:
         out = np.kron(out, factor)
     return out
 
 
-def is_power_of_two(n: int) -> bool:
-    return n != 0 and (n & (n - 1)) == 0
+def is_power_of_two(n):
+    return n > 0 and bin(n).count("1") == 1 if isinstance(n, (int, np.integer)) else (n != 0 and (n & (n - 1)) == 0)
 
 
-def is_qubit_operator(oper: np.ndarray) -> bool:
+def is_qubit_operator(oper):
     return oper.ndim == 2 and oper.shape[0] == oper.shape[1] and is_power_of_two(oper.shape[0])
 
 
-def is_qubit_state(state: np.ndarray) -> bool:
+def is_qubit_state(state):
     return state.ndim == 1 and is_power_of_two(len(state))
 
 
-def is_hermitian(oper: np.ndarray) -> bool:
-    return np.allclose(dagger(oper), oper)
+def is_hermitian(oper):
+    return np.allclose(oper, oper.conj().T)
 
 
-def expect(oper: np.ndarray, state: np.ndarray):
-    if not (is_qubit_operator(oper) and is_qubit_state(state) and oper.shape[0] == state.shape[0]):
+def expect(oper, state):
+    compatible = is_qubit_operator(oper) and is_qubit_state(state) and oper.shape[0] == state.shape[0]
+    if not compatible:
         raise TypeError("incompatible operator and state vector")
-    return np.conjugate(state) @ oper @ state
+    return np.vdot(state, oper @ state)
 
 
-def expecth(oper: np.ndarray, state: np.ndarray):
-    return expect(oper, state).real
+def expecth(oper, state):
+    """Real part of the expectation value (Hermitian operators)."""
+    value = expect(oper, state)
+    return value.real
 
 
-def rand_ket(d=2) -> np.ndarray:
-    return normalise(np.random.rand(d) + 1j * np.random.rand(d))
+def rand_ket(d=2):
+    real, imag = np.random.rand(d), np.random.rand(d)       # two draws from the global generator, in this order
+    return normalise(real + 1j * imag)
 
 
-def dagger(array: np.ndarray) -> np.ndarray:
-    return np.conjugate(array.T)
+def dagger(array):
+    return array.conj().T
 
 
 def num_qubits(arr) -> int:
-    size = arr if isinstance(arr, int) else arr.shape[0]
-    return int(np.log2(size))
+    """log2 of a dimension (given directly or as the leading extent of an array)."""
+    return int(np.log2(arr if isinstance(arr, int) else arr.shape[0]))
 
 
-def permute_tensor_product(array: np.ndarray, new_ordering) -> np.ndarray:
+def permute_tensor_product(array, new_ordering):
     """Move tensor factor j to position ``new_ordering[j]`` (rows, and columns
     too for operators) -- numpy_quantum.py:227-240."""
     if not is_power_of_two(array.shape[0]):
@@ -281,7 +300,7 @@ def permute_tensor_product(array: np.ndarray, new_ordering) -> np.ndarray:
     return back.reshape((2 ** nq, -1)).T
 
 
-def expand_gate(gate: np.ndarray, N: int, targets) -> np.ndarray:
+def expand_gate(gate, N, targets):
     """Dense (2^N, 2^N) operator (numpy_quantum.py:243-247).  O(4^N): kept for
     compatibility and small N only; the simulator itself never calls it."""
     targets = list(targets)
