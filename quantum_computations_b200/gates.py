@@ -131,15 +131,6 @@ def _one_qubit_class(name: str, build):
     return type(name, (SingleQubitGate,), {"__init__": __init__, "__module__": __name__, "__qualname__": name})
 
 
-def _two_qubit_class(name: str, build, first: str, second: str, extras=None):
-    # the argument names are part of the surface (keyword calls): built with exec to keep them
-    namespace = {"TwoQubitGate": TwoQubitGate, "_build": build}
-    exec(f"def __init__(self, {first}, {second}):\n    TwoQubitGate.__init__(self, {first}, {second}, _build())", namespace)
-    body = {"__init__": namespace["__init__"], "__module__": __name__, "__qualname__": name}
-    body.update(extras or {})
-    return type(name, (TwoQubitGate,), body)
-
-
 _ONE_QUBIT_TABLE = {
     "I": lambda: npq.IDTY, "X": lambda: npq.X, "Y": lambda: npq.Y, "Z": lambda: npq.Z, "H": lambda: npq.H,
     "P": lambda: _z_rotation(np.pi / 2), "Pdg": lambda: _z_rotation(-np.pi / 2),
@@ -147,11 +138,26 @@ _ONE_QUBIT_TABLE = {
 }
 I, X, Y, Z, H, P, Pdg, T, Tdg = (_one_qubit_class(_name, _build) for _name, _build in _ONE_QUBIT_TABLE.items())
 
-CX = _two_qubit_class("CX", lambda: npq.CX, "control", "target",
-                      {"control": property(lambda self: self.indices[0]),
-                       "target": property(lambda self: self.indices[1])})
-CZ = _two_qubit_class("CZ", lambda: npq.CZ, "index1", "index2")
-SWAP = _two_qubit_class("SWAP", lambda: npq.SWAP, "index1", "index2")
+
+
+class CX(TwoQubitGate):
+    """Controlled X; the argument names are part of the surface (keyword calls)."""
+
+    def __init__(self, control, target):
+        TwoQubitGate.__init__(self, control, target, npq.CX)
+
+    control = property(lambda self: self.indices[0])
+    target = property(lambda self: self.indices[1])
+
+
+class CZ(TwoQubitGate):
+    def __init__(self, index1, index2):
+        TwoQubitGate.__init__(self, index1, index2, npq.CZ)
+
+
+class SWAP(TwoQubitGate):
+    def __init__(self, index1, index2):
+        TwoQubitGate.__init__(self, index1, index2, npq.SWAP)
 
 
 class RZ(SingleQubitGate):
