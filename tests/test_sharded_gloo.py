@@ -17,6 +17,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _emulator_built_once():
+    """Build the emulator library in the parent, so that the spawned ranks only load it."""
+    sys.path.insert(0, ROOT)
+    from quantum_computations_b200.build_native import build_emu
+    build_emu()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
