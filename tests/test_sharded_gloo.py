@@ -263,6 +263,21 @@ def _exchange_worker(rank, world, port, n, out_dir):
             st.exchange(pairs)
             if not np.array_equal(st.gather_numpy(), want):              # the logical state never changes
                 bad += 1
+        # reductions over ranks: <a|b> and |<a|b>|^2 of two states in the same (permuted) layout
+        other = sharded.ShardedState(n, comm, backend=emu(), as_torch=torch.from_numpy)
+        other.phys, other.flip = list(st.phys), list(st.flip)
+        rng = np.random.default_rng(5)
+        full_b = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        # lay `full_b` (logical order) out like st: physical index p takes logical index l with bit moves
+        idx = np.arange(1 << n)
+        logical_of_phys = np.zeros_like(idx)
+        for l, p in enumerate(st.phys):
+            logical_of_phys |= ((idx >> p) & 1) << l
+        other.buf[:] = full_b[logical_of_phys][rank * size:(rank + 1) * size]
+        inner = st.inner(other)
+        want_inner = np.vdot(want, full_b)
+        if abs(inner - want_inner) > 1e-9 * abs(want_inner) or abs(st.fidelity(other) - abs(want_inner) ** 2) > 1e-9 * abs(want_inner) ** 2:
+            bad += 1
         if rank == 0:
             np.save(os.path.join(out_dir, "exchange.npy"), np.array([bad, st.swaps, sorted(st.phys) == list(range(n))]))
     finally:
