@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--max-group", type=int, default=0)
     ap.add_argument("--max-dense", type=int, default=0)
     ap.add_argument("--lookahead", type=int, default=0)
+    ap.add_argument("--max-layers", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
@@ -151,7 +152,7 @@ def cpu_baseline(seconds: float, seed: int) -> dict:
 
 def plan_options(args) -> dict:
     return {"tile_bits": args.tile_bits, "low_bits": args.low_bits, "max_group": args.max_group,
-            "max_dense_ops": args.max_dense, "lookahead": args.lookahead}
+            "max_dense_ops": args.max_dense, "lookahead": args.lookahead, "max_layers": args.max_layers}
 
 
 # ---- reference arm -----------------------------------------------------------------------------------

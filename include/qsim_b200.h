@@ -48,7 +48,8 @@ typedef struct {
   int32_t defer_tail;       /* 1 = do not apply the trailing diagonal / antidiagonal single-qubit
                                products; hand them back through qsim_plan_residual so that the
                                caller can merge them into its next plan (needs merge_1q on)      */
-  int32_t reserved0;
+  int32_t max_layers;       /* gate layers per shared-memory round trip (1..8): a qubit whose
+                               amplitudes are in registers can take its next gates there;  0 = default */
   uint64_t apply_tail_mask; /* with defer_tail: qubits (bit q = qubit q) whose trailing products are
                                applied all the same                                              */
 } qsim_plan_options_t;
@@ -60,8 +61,9 @@ typedef struct {
   int64_t n_steps;          /* shared-memory round trips over all passes                        */
   int64_t n_dense;          /* matrix applications inside the steps                             */
   int64_t n_sign;           /* CZ/Z sign pairs                                                  */
-  int64_t n_generic;        /* gates on > 4 qubits executed by the out-of-place generic kernel  */
+  int64_t n_generic;        /* gates on 5..10 qubits: one in-place dense-block launch each (DMMA) */
   int64_t n_warp_syncs;     /* steps followed by a warp-level instead of a block-level barrier  */
+  int64_t n_layers;         /* gate layers over all steps (n_layers >= n_steps)                 */
 } qsim_plan_stats_t;
 
 const char* qsim_last_error(void);
@@ -85,7 +87,7 @@ void qsim_circuit_destroy(qsim_circuit_t* c);
 
 int qsim_plan_compile(const qsim_circuit_t* c, const qsim_plan_options_t* opt, qsim_plan_t** out);
 int qsim_plan_stats(const qsim_plan_t* p, qsim_plan_stats_t* out);
-/* scratch: device buffer of 2^n amplitudes, needed only when stats.n_generic > 0 */
+/* scratch: unused (kept for ABI stability; every kernel works in place), may be NULL */
 int qsim_plan_execute(const qsim_plan_t* p, void* state, int n_qubits, void* scratch, void* stream);
 /* With options.defer_tail: the single-qubit gate left over on every qubit, n_qubits x (2x2
  * row-major complex) = 8 doubles per qubit, qubit 0 first; identity where nothing is left.

@@ -22,7 +22,7 @@ class PlanOptions(C.Structure):
         ("lookahead", C.c_int32),
         ("merge_1q", C.c_int32),
         ("defer_tail", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("max_layers", C.c_int32),
         ("apply_tail_mask", C.c_uint64),
     ]
 
@@ -37,6 +37,7 @@ class PlanStats(C.Structure):
         ("n_sign", C.c_int64),
         ("n_generic", C.c_int64),
         ("n_warp_syncs", C.c_int64),
+        ("n_layers", C.c_int64),
     ]
 
     def as_dict(self) -> dict:

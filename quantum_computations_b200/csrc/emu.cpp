@@ -34,9 +34,9 @@ void slots_of_step(const QsPass& P, int s, const QsStepTab& tab, std::vector<int
   const uint32_t nwork = 1u << (P.T - st.r);
   owner.assign((size_t)1 << P.T, -1);
   for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
-    const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
+    const uint32_t jlo = qs_thread_jlo(tab, tid);
     for (uint32_t i = 0, w = tid; w < nwork; ++i, w += QS_THREADS) {
-      const uint32_t j0 = jlo | (tab.hi[i] & 0xffffu);
+      const uint32_t j0 = jlo | (st.hi[i] & 0xffffu);
       for (int m = 0; m < (1 << st.r); ++m) {
         uint32_t d = 0;
         for (int f = 0; f < st.r; ++f) d |= (uint32_t)((m >> (st.r - 1 - f)) & 1) << st.gpos[f];
@@ -52,6 +52,9 @@ void check_warp_ownership(const QsPass& P, int s, const QsStepTab& tab_s) {
   static const QsPass* prev_pass = nullptr;
   std::vector<int> cur;
   slots_of_step(P, s, tab_s, cur);
+  // every slot of the tile must be touched exactly by one work item
+  for (size_t j = 0; j < cur.size(); ++j)
+    if (cur[j] < 0) { ++g_ownership_violations; break; }
   if (prev_pass == &P && prev_step == s - 1 && P.steps[s - 1].block_sync == 0)
     for (size_t j = 0; j < cur.size(); ++j)
       if (cur[j] != prev[j]) { ++g_ownership_violations; break; }
@@ -64,57 +67,47 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   const uint64_t ntiles = 1ull << (n - (int)P.T);
   const int nsteps = (int)P.nsteps;
   std::vector<qs_c128> tile((size_t)1 << P.T);
-  std::vector<uint32_t> zmask(nsteps + 2, 0);
+  std::vector<uint32_t> zm(P.nlayers + 1, 0);
   std::vector<QsStepTab> tab(nsteps ? nsteps : 1);
-  QsIoTab io;
   bool dense = false;
-  for (int s = 0; s < nsteps; ++s) {
-    dense |= P.steps[s].kind == QS_STEP_DENSE;
+  for (uint32_t l = 0; l < P.nlayers; ++l) dense |= P.layers[l].kind == QS_LAYER_DENSE;
+  for (int s = 0; s < nsteps; ++s)
     for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
-  }
-  for (uint32_t i = 0; i < QS_MAX_ITER; ++i) qs_build_io_tab(P, i, &io, QS_THREADS_LOG2);
-  io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
-  for (uint32_t e = 0; e < 256; ++e) qs_build_base_tab(P, e, &io);
-  const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
-  std::vector<uint64_t> glo(QS_THREADS);
-  std::vector<uint32_t> fin_qlo(QS_THREADS);
-  for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
-    glo[tid] = qs_scatter64(tid, P.tile_bits, lo_bits);
-    fin_qlo[tid] = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
-  }
-  for (uint64_t t = 0; t < ntiles; ++t) {
-    const uint64_t base = qs_tile_base_tab(P, io, t);
-    for (int s = 0; s < nsteps; ++s)
-      if (P.steps[s].has_sign) zmask[s] = qs_step_zg(P, s, base);
-    if (P.fin_has_sign) qs_fin_prepare(P, base, &zmask[nsteps], &zmask[nsteps + 1]);
+  std::vector<uint32_t> fin_qlo(QS_THREADS, 0);
+  if (P.has_final)
     for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_load(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io,
-                    [](void* dst, const void* src) { *(qs_c128*)dst = *(const qs_c128*)src; });
+      fin_qlo[tid] = qs_fin_quad(P, qs_thread_jlo(tab[nsteps - 1], tid));
+  for (uint64_t t = 0; t < ntiles; ++t) {
+    const uint64_t base = qs_tile_base(P, t);
+    for (int l = 0; l < (int)P.nlayers; ++l)
+      zm[l] = (P.layers[l].flags & QS_LF_SIGN) ? qs_layer_z(P, l, base) : 0u;
+    const uint32_t fin_g = P.has_final ? qs_fin_g(P, base) : 0u;
+    for (uint32_t tid = 0; tid < QS_THREADS; ++tid) qs_plain_load(P, state, tile.data(), base, tid, QS_THREADS);
     for (int s = 0; s < nsteps; ++s) {
       for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
         // same variant selection as launch_pass() in kernels.cu
-        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
-        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zmask[s], tab[s]);
+        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
       }
       if (t == 0) check_warp_ownership(P, s, tab[s]);
     }
-    for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
-      qs_phase_store(P, state, tile.data(), base, tid, QS_THREADS_LOG2, glo[tid], io, fin_qlo[tid],
-                     zmask[nsteps], zmask[nsteps + 1]);
+    for (uint32_t tid = 0; tid < QS_THREADS; ++tid) qs_plain_store(P, state, tile.data(), base, tid, QS_THREADS);
   }
   ++g_launches;
 }
 
-int emu_generic(const qs::Op& op, qs_c128* state, qs_c128* scratch, int n) {
-  if (!scratch) return qs::fail(QSIM_ERR_ARG, "a gate on more than 4 qubits needs a scratch buffer of 2^n amplitudes");
+// dense block on more than QS_MAX_R qubits: the CUDA library runs it in place (k_dense_block);
+// here the plain definition with a temporary copy
+int emu_generic(const qs::Op& op, qs_c128* state, int n) {
   const int dim = 1 << op.k;
   std::vector<double> flat(2 * (size_t)dim * dim);
   for (int e = 0; e < dim * dim; ++e) { flat[2 * e] = op.mat[e].real(); flat[2 * e + 1] = op.mat[e].imag(); }
   int bits[10];
   for (int f = 0; f < op.k; ++f) bits[f] = op.bits[f];
   const uint64_t count = 1ull << n;
+  std::vector<qs_c128> scratch(count);
   for (uint64_t i = 0; i < count; ++i) scratch[i] = qs_generic_amp(state, flat.data(), bits, op.k, i);
-  memcpy(state, scratch, sizeof(qs_c128) * count);
+  memcpy(state, scratch.data(), sizeof(qs_c128) * count);
   ++g_launches;
   return QSIM_OK;
 }
@@ -126,7 +119,7 @@ int execute_plan(const qsim_plan* p, void* state, int n, void* scratch) {
   if (n != p->n) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: plan was compiled for a different qubit count");
   for (const qs::PlanItem& it : p->items) {
     if (it.generic) {
-      int rc = emu_generic(it.op, (qs_c128*)state, (qs_c128*)scratch, n);
+      int rc = emu_generic(it.op, (qs_c128*)state, n);
       if (rc != QSIM_OK) return rc;
     } else {
       if ((int)it.pass.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
@@ -430,9 +423,9 @@ int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
               for (int l = 0; l < 8; ++l) {
                 const uint32_t tid = warp * 32 + quarter * 8 + l;
                 if (tid + i * QS_THREADS >= nwork) continue;
-                const uint32_t jlo = (uint32_t)tab.jA[tid & 15u] | (uint32_t)tab.jB[(tid >> 4) & 31u];
+                const uint32_t jlo = qs_thread_jlo(tab, tid);
                 const uint32_t slo = qs_swz(jlo);
-                const uint32_t byte = ((slo ^ (tab.hi[i] >> 16)) << 4) ^ tab.sdepb[m];
+                const uint32_t byte = ((slo ^ (st.hi[i] >> 16)) << 4) ^ st.sdepb[m];
                 worst = std::max(worst, ++count[(byte >> 4) & 7u]);
               }
               total += worst;
@@ -459,7 +452,11 @@ int qsim_emu_plan_shape(const qsim_plan_t* p, int* out, int max_passes) {
   for (const qs::PlanItem& it : p->items) {
     if (it.generic || k >= max_passes) continue;
     int mats = 0;
-    for (uint32_t s = 0; s < it.pass.nsteps; ++s) mats += it.pass.steps[s].kind == QS_STEP_1Q ? it.pass.steps[s].r : 1;
+    for (uint32_t l = 0; l < it.pass.nlayers; ++l) {
+      const QsLayer& L = it.pass.layers[l];
+      if (L.kind == QS_LAYER_DENSE) { ++mats; continue; }
+      for (int f = 0; f < QS_MAX_R; ++f) mats += L.form[f] != QS_FORM_NONE ? 1 : 0;
+    }
     out[3 * k] = (int)it.pass.nsteps;
     out[3 * k + 1] = mats;
     out[3 * k + 2] = (int)it.pass.npairs;

@@ -4,12 +4,18 @@
 // stores per amplitude, shared-memory staging of 2^T-amplitude tiles so several
 // gates apply per HBM pass, persistent grids sized to the SM count.  No tensor
 // cores: tcgen05 has no f64 kind and the 2x2/4x4 updates have no GEMM shape.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
 
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
@@ -23,11 +29,16 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 
 struct DevCtx {
-  bool ready = false;
+  std::once_flag once;
+  int init_rc = 0;                // cudaError_t of the one-time initialisation
   int sms = 0;
+  // scratch of the reductions: one set per device, serialised by reduce_lock (a reduction
+  // synchronises its stream anyway, so concurrent callers lose nothing)
+  std::mutex reduce_lock;
   double* d_partials = nullptr;   // [kReduceBlocks][2]
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
+  std::mutex occ_lock;
   int occ[4] = {0, 0, 0, 0};      // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
@@ -44,7 +55,18 @@ DevCtx g_ctx[kMaxDevices];
       return qs::fail(QSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-int bind_device(const void* ptr, DevCtx** ctx) {
+// The device a buffer lives on, made current for the lifetime of this object (the caller's
+// current device is restored afterwards: torch keeps its own idea of it).
+struct Bound {
+  DevCtx* ctx = nullptr;
+  int device = -1;
+  int prev = -1;
+  ~Bound() {
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  }
+};
+
+int bind_device(const void* ptr, Bound* b) {
   cudaPointerAttributes at;
   cudaError_t e = cudaPointerGetAttributes(&at, ptr);
   if (e != cudaSuccess) {
@@ -54,152 +76,273 @@ int bind_device(const void* ptr, DevCtx** ctx) {
   if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
     return qs::fail(QSIM_ERR_ARG, "buffer is not device memory (no CPU path exists in this library)");
   if (at.device < 0 || at.device >= kMaxDevices) return qs::fail(QSIM_ERR_ARG, "device index out of range");
-  QS_CUDA(cudaSetDevice(at.device));
+  if (cudaGetDevice(&b->prev) != cudaSuccess) b->prev = -1;
+  b->device = at.device;
+  if (b->prev != at.device) QS_CUDA(cudaSetDevice(at.device));
   DevCtx& c = g_ctx[at.device];
-  if (!c.ready) {
+  std::call_once(c.once, [&c, &at] {
     cudaDeviceProp prop;
-    QS_CUDA(cudaGetDeviceProperties(&prop, at.device));
-    c.sms = prop.multiProcessorCount;
-    QS_CUDA(cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks));
-    QS_CUDA(cudaMalloc(&c.d_out, sizeof(double) * 2));
-    QS_CUDA(cudaMallocHost(&c.h_out, sizeof(double) * 2));
-    // stream-ordered allocations (generic-gate path) keep their memory between calls instead
-    // of handing it back to the driver at every synchronisation
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, at.device) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    cudaGetLastError();
-    c.ready = true;
-  }
-  *ctx = &c;
+    cudaError_t rc = cudaGetDeviceProperties(&prop, at.device);
+    if (rc == cudaSuccess) c.sms = prop.multiProcessorCount;
+    if (rc == cudaSuccess) rc = cudaMalloc(&c.d_partials, sizeof(double) * 2 * kReduceBlocks);
+    if (rc == cudaSuccess) rc = cudaMalloc(&c.d_out, sizeof(double) * 2);
+    if (rc == cudaSuccess) rc = cudaMallocHost(&c.h_out, sizeof(double) * 2);
+    c.init_rc = (int)rc;
+  });
+  if (c.init_rc != 0)
+    return qs::fail(QSIM_ERR_CUDA, std::string("device initialisation: ") + cudaGetErrorString((cudaError_t)c.init_rc));
+  b->ctx = &c;
   return QSIM_OK;
 }
 
 // =====================================================================================
 // Tile pass: the fused multi-gate kernel (plan.h / tile_exec.h)
 // =====================================================================================
-// 16-byte asynchronous global->shared copy (LDGSTS): no register staging, and the
-// thread does not wait, so the next tile streams in while the current one computes.
-struct CopyAsync16 {
-  __device__ __forceinline__ void operator()(void* dst, const void* src) const {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
-  }
-};
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// TMA + mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UTMASTG / SYNCS).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One pass of the fused plan.  Persistent grid: every CTA loops over tiles.  With
-// `dbuf` the dynamic shared memory holds two tile buffers and the loads of tile
-// k+1 are issued before the steps of tile k run.
+// Box `o` of the tile at `base`: its tile positions P.. are the bits of o.
+__device__ __forceinline__ void tma_box_coords(const QsPass& P, const QsTmaGeom& G, uint64_t base, int o, int* c) {
+  uint64_t b = base;
+  for (int q = 0; q < (int)P.T - G.P; ++q) b |= (uint64_t)((o >> q) & 1) << P.tile_bits[G.P + q];
+  c[0] = (int)(((b >> G.shift[0]) & G.mask[0]) * 2);       // dimension 0 counts doubles
+#pragma unroll
+  for (int i = 1; i < 5; ++i) c[i] = (int)((b >> G.shift[i]) & G.mask[i]);
+}
+
+// One pass of the fused plan.  Persistent grid: every CTA loops over tiles; TMA brings a
+// tile into shared memory (one mbarrier per CTA), the steps run on it, TMA writes it back.
+// The three CTAs of an SM are in different phases, so one CTA's fill and drain overlap
+// the steps of the other two.
 template <int MAXR, bool DENSE>
-__global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1)
-                                               : QS_THREADS_LOG2 <= 7 ? 3 : (MAXR <= 3 ? 3 : 2)))
-k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, uint64_t ntiles, int dbuf, int debug_skip) {
-  extern __shared__ __align__(16) unsigned char qs_smem[];
-  qs_c128* buf0 = reinterpret_cast<qs_c128*>(qs_smem);
-  qs_c128* buf1 = buf0 + (dbuf ? (1u << P.T) : 0u);
+__global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
+k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_constant__ CUtensorMap tmap,
+            const __grid_constant__ QsTmaGeom G, uint64_t ntiles) {
+  extern __shared__ __align__(1024) unsigned char qs_smem[];
+  qs_c128* tile = reinterpret_cast<qs_c128*>(qs_smem);
   __shared__ QsStepTab s_tab[QS_MAX_STEPS];
-  __shared__ QsIoTab s_io;
-  __shared__ uint32_t s_zmask[QS_MAX_STEPS + 2];   // [nsteps], then final z, final g
+  __shared__ uint32_t s_zm[QS_MAX_LAYERS + 1];     // per layer qs_layer_z; [QS_MAX_LAYERS] = final g
+  __shared__ __align__(8) uint64_t s_bar;
   const uint32_t tid = threadIdx.x;
   const int nsteps = (int)P.nsteps;
+  const int nlayers = (int)P.nlayers;
+  const bool use_tma = G.use_tma != 0;
 
-  // tile-independent tables, once per launch (the grid is persistent)
+  // tile-independent thread tables, once per launch (the grid is persistent)
   for (int e = (int)tid; e < nsteps * QS_TAB_ENTRIES; e += QS_THREADS)
     qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
-  if (tid < QS_MAX_ITER) qs_build_io_tab(P, tid, &s_io, QS_THREADS_LOG2);
-  if (tid == QS_MAX_ITER) s_io.fin_q = qs_build_fin_q(P, QS_THREADS_LOG2);
-  for (uint32_t e = tid; e < 256; e += QS_THREADS) qs_build_base_tab(P, e, &s_io);
-  const int lo_bits = (int)(P.T < QS_THREADS_LOG2 ? P.T : QS_THREADS_LOG2);
-  const uint64_t glo = qs_scatter64(tid, P.tile_bits, lo_bits);
-  const uint32_t fin_qlo = P.fin_has_sign ? qs_fin_quad(P, tid & ((1u << P.T) - 1u)) : 0u;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  const uint32_t fin_qlo = P.has_final ? qs_fin_quad(P, qs_thread_jlo(s_tab[nsteps - 1], tid)) : 0u;
+  uint32_t phase = 0;
+  const uint32_t box_bytes = 16u << G.P;
 
-  uint64_t t = blockIdx.x;
-  if (dbuf && t < ntiles)
-    qs_phase_load(P, state, buf0, qs_tile_base_tab(P, s_io, t), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
-  cp_async_commit();
-
-  for (uint32_t k = 0; t < ntiles; t += gridDim.x, ++k) {
-    qs_c128* cur = (dbuf && (k & 1u)) ? buf1 : buf0;
-    qs_c128* nxt = (k & 1u) ? buf0 : buf1;
-    const uint64_t base = qs_tile_base_tab(P, s_io, t);
-    if ((int)tid < nsteps) {
-      if (P.steps[tid].has_sign) s_zmask[tid] = qs_step_zg(P, (int)tid, base);
-    } else if ((int)tid == nsteps && P.fin_has_sign) {
-      qs_fin_prepare(P, base, &s_zmask[nsteps], &s_zmask[nsteps + 1]);
-    }
-    if (dbuf) {
-      const uint64_t tn = t + gridDim.x;
-      if (tn < ntiles)
-        qs_phase_load(P, state, nxt, qs_tile_base_tab(P, s_io, tn), tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
-      cp_async_commit();
-      cp_async_wait<1>();          // everything but the prefetch just issued has landed
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint64_t base = 0;
+    if (!use_tma || tid < 96) base = qs_tile_base(P, t);
+    if (use_tma) {
+      if (tid < 32) {
+        tma_wait_read0();                        // my stores of the previous tile have left the buffer
+        __syncwarp();
+        if (tid == 0) mbar_expect_tx(&s_bar, 16u << P.T);
+        __syncwarp();
+        for (int o = (int)tid; o < G.nops; o += 32) {
+          int c[5];
+          tma_box_coords(P, G, base, o, c);
+          tma_load_5d(qs_smem + (size_t)o * box_bytes, &tmap, &s_bar, c[0], c[1], c[2], c[3], c[4]);
+        }
+      }
     } else {
-      if (!(debug_skip & 1)) qs_phase_load(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, CopyAsync16());
-      cp_async_commit();
-      cp_async_wait<0>();
+      qs_plain_load(P, state, tile, base, tid, QS_THREADS);
+    }
+    // per-tile sign data, one thread per layer (warps 1 and 2)
+    if (tid >= 32 && (int)tid < 32 + nlayers) {
+      const int l = (int)tid - 32;
+      if (P.layers[l].flags & QS_LF_SIGN) s_zm[l] = qs_layer_z(P, l, base);
+    } else if (tid == 95 && P.has_final) {
+      s_zm[QS_MAX_LAYERS] = qs_fin_g(P, base);
     }
     __syncthreads();
+    if (use_tma) {
+      while (!mbar_try_wait(&s_bar, phase)) {}
+      phase ^= 1u;
+    }
+    const uint32_t fin_g = s_zm[QS_MAX_LAYERS];
     for (int s = 0; s < nsteps; ++s) {
-      qs_phase_step_any<MAXR, DENSE>(P, s, cur, tid, QS_THREADS_LOG2, s_zmask[s], s_tab[s], debug_skip);
+      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zm, fin_g, fin_qlo, s_tab[s]);
+      // the tile goes back through the async proxy: order this thread's writes before it
+      if (s == nsteps - 1 && use_tma) fence_async_smem();
       // inside a run the next step touches only amplitudes of the same warp (plan.h)
       if (P.steps[s].block_sync) __syncthreads();
       else __syncwarp();
     }
-    if (!(debug_skip & 2))
-      qs_phase_store(P, state, cur, base, tid, QS_THREADS_LOG2, glo, s_io, fin_qlo, s_zmask[nsteps],
-                     s_zmask[nsteps + 1]);
-    __syncthreads();
+    if (use_tma) {
+      if (tid < 32) {
+        for (int o = (int)tid; o < G.nops; o += 32) {
+          int c[5];
+          tma_box_coords(P, G, base, o, c);
+          tma_store_5d(&tmap, qs_smem + (size_t)o * box_bytes, c[0], c[1], c[2], c[3], c[4]);
+        }
+        tma_commit();
+      }
+    } else {
+      qs_plain_store(P, state, tile, base, tid, QS_THREADS);
+      __syncthreads();
+    }
   }
-  cp_async_wait<0>();
+  if (use_tma && tid < 32) tma_wait_read0();
 }
 
-typedef void (*TileKernel)(qs_c128*, const QsPass, uint64_t, int, int);
+typedef void (*TileKernel)(qs_c128*, const QsPass, const CUtensorMap, const QsTmaGeom, uint64_t);
+
+PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (PFN_cuTensorMapEncodeTiled)p;
+  }();
+  return fn;
+}
+
+// Describe the state to TMA so that one box covers the lowest tile positions of the pass
+// (plan.h, QsTmaGeom).  Dimension 0 is the index-bit range [0, cut1) with a box of bits
+// 0..2 (one 128-byte row, the swizzle span); dimensions 1..4 start at the four lowest runs
+// of tile bits above bit 2 (a run longer than 8 bits is cut: boxes are at most 256 wide).
+// Returns use_tma = 0 when the pass has to use plain loads.
+void make_tma_geom(const QsPass& P, qs_c128* state, int n, QsTmaGeom* G, CUtensorMap* map) {
+  memset(G, 0, sizeof(*G));
+  memset(map, 0, sizeof(*map));
+  static const bool off = [] { const char* e = getenv("QSIM_NO_TMA"); return e && atoi(e) != 0; }();
+  PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+  const int T = (int)P.T;
+  if (off || !enc || n < 12 || n > 40 || T < 6) return;
+  if (P.tile_bits[0] != 0 || P.tile_bits[1] != 1 || P.tile_bits[2] != 2) return;
+  bool is_tile[64] = {false};
+  for (int l = 0; l < T; ++l) is_tile[P.tile_bits[l]] = true;
+  int cuts[4], ncuts = 0;
+  {
+    int run = 0;
+    for (int b = 3; b < n && ncuts < 4; ++b) {
+      if (is_tile[b] && (run == 0 || run == 8)) { cuts[ncuts++] = b; run = 1; }
+      else if (is_tile[b]) ++run;
+      else run = 0;
+    }
+    for (int b = n - 1; b > 3 && ncuts < 4; --b) {     // fillers: any other positions
+      bool used = false;
+      for (int i = 0; i < ncuts; ++i) used |= cuts[i] == b;
+      if (!used) cuts[ncuts++] = b;
+    }
+    if (ncuts != 4) return;
+    std::sort(cuts, cuts + 4);
+  }
+  const int start[6] = {0, cuts[0], cuts[1], cuts[2], cuts[3], n};
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  int covered = 3;
+  bool prefix = true;         // the box must cover the LOWEST tile positions, in order
+  for (int i = 0; i < 5; ++i) {
+    const int lo = start[i], hi = start[i + 1];
+    if (hi - lo > 31) return;
+    int nb = 0;
+    if (i == 0) {
+      nb = 3;
+      for (int b = 3; b < hi; ++b)
+        if (is_tile[b]) return;                        // cannot happen: cut 1 is the first tile bit above 2
+    } else {
+      if (prefix)
+        while (lo + nb < hi && is_tile[lo + nb] && nb < 8) ++nb;
+      for (int b = lo + nb; b < hi; ++b)
+        if (is_tile[b]) prefix = false;
+      covered += nb;
+    }
+    G->shift[i] = lo;
+    G->mask[i] = (uint32_t)((1ull << (hi - lo)) - 1ull);
+    gdim[i] = (1ull << (hi - lo)) * (i == 0 ? 2 : 1);
+    box[i] = (1u << nb) * (i == 0 ? 2 : 1);
+    if (i > 0) gstride[i - 1] = 16ull << lo;
+  }
+  if (covered < 6 || T - covered > 6) return;
+  if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return;
+  G->P = covered;
+  G->nops = 1 << (T - covered);
+  G->use_tma = 1;
+}
 
 int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_t stream) {
   if ((int)P.T > n) return qs::fail(QSIM_ERR_ARG, "pass tile larger than the state");
   const uint64_t ntiles = 1ull << (n - (int)P.T);
-  // double-buffer when two tiles still leave room for three CTAs per SM (T <= 11);
-  // QSIM_DBUF=0/1 overrides for experiments
-  static const int dbuf_env = [] {
-    const char* e = getenv("QSIM_DBUF");
-    return e ? atoi(e) : -1;
-  }();
-  const int dbuf = dbuf_env >= 0 ? (dbuf_env != 0) : (P.T <= 11);
-  const int smem = (int)(sizeof(qs_c128) << P.T) * (dbuf ? 2 : 1);
+  const int smem = (int)(sizeof(qs_c128) << P.T);
   int maxr = 1;
   bool dense = false;
-  for (uint32_t s = 0; s < P.nsteps; ++s) {
-    maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
-    dense |= P.steps[s].kind == QS_STEP_DENSE;
-  }
+  for (uint32_t s = 0; s < P.nsteps; ++s) maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
+  for (uint32_t l = 0; l < P.nlayers; ++l) dense |= P.layers[l].kind == QS_LAYER_DENSE;
   static const TileKernel variants[4] = {k_tile_pass<3, false>, k_tile_pass<3, true>,
                                          k_tile_pass<4, false>, k_tile_pass<4, true>};
   const int vi = (maxr <= 3 ? 0 : 2) + (dense ? 1 : 0);
-  if (ctx->occ_smem != smem) {
-    for (int v = 0; v < 4; ++v) {
-      QS_CUDA(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], QS_THREADS, smem));
+  int occ;
+  {
+    std::lock_guard<std::mutex> guard(ctx->occ_lock);
+    if (ctx->occ_smem != smem) {
+      for (int v = 0; v < 4; ++v) {
+        QS_CUDA(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], QS_THREADS, smem));
+      }
+      ctx->occ_smem = smem;
     }
-    ctx->occ_smem = smem;
+    occ = ctx->occ[vi];
   }
-  const int occ = ctx->occ[vi];
   if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "tile pass does not fit on an SM");
   uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
   if (grid > ntiles) grid = ntiles;
-  // QSIM_DEBUG_SKIP (development only): bit 0 skips the global loads, bit 1 the global
-  // stores of a pass, bit 2 the matrix arithmetic, to time the parts on their own
-  // (results are garbage)
-  static const int debug_skip = [] {
-    const char* e = getenv("QSIM_DEBUG_SKIP");
-    return e ? atoi(e) : 0;
-  }();
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, ntiles, dbuf, debug_skip);
+  QsTmaGeom geom;
+  CUtensorMap map;
+  make_tma_geom(P, state, n, &geom, &map);
+  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, map, geom, ntiles);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;
@@ -264,15 +407,6 @@ __global__ void k_insert(const qs_c128* __restrict__ in, qs_c128* __restrict__ o
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
        i += (uint64_t)gridDim.x * blockDim.x)
     out[i] = qs_insert_amp(in, pos, i, amp.b);
-}
-
-struct BitList { int bits[10]; };
-
-__global__ void k_generic(const qs_c128* __restrict__ in, qs_c128* __restrict__ out,
-                          const double* __restrict__ mat, BitList bl, int k, uint64_t count) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    out[i] = qs_generic_amp(in, mat, bl.bits, k, i);
 }
 
 __global__ void k_swap_pack(const qs_c128* __restrict__ shard, qs_c128* __restrict__ buf, QsBitSel sel,
@@ -400,6 +534,7 @@ int reduce_to_host(DevCtx* ctx, F f, uint64_t count, double* out2, cudaStream_t 
   uint64_t blocks = (count + kReduceThreads - 1) / kReduceThreads;
   if (blocks > (uint64_t)kReduceBlocks) blocks = kReduceBlocks;
   if (blocks < 1) blocks = 1;
+  std::lock_guard<std::mutex> guard(ctx->reduce_lock);
   k_reduce<F><<<(unsigned)blocks, kReduceThreads, 0, stream>>>(f, count, ctx->d_partials);
   k_reduce_final<<<1, kReduceThreads, 0, stream>>>(ctx->d_partials, (int)blocks, ctx->d_out);
   g_launches.fetch_add(2, std::memory_order_relaxed);
@@ -429,36 +564,143 @@ __global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint16_t*
                       out_rho ? out_rho + (size_t)b * 2 * DIM * DIM : nullptr);
 }
 
-int run_generic(DevCtx* ctx, const qs::Op& op, qs_c128* state, qs_c128* scratch, int n, cudaStream_t stream) {
-  if (!scratch) return qs::fail(QSIM_ERR_ARG, "a gate on more than 4 qubits needs a scratch buffer of 2^n amplitudes");
-  const int dim = 1 << op.k;
-  const size_t bytes = sizeof(double) * 2 * dim * dim;
-  std::vector<double> flat(2 * (size_t)dim * dim);
-  for (int e = 0; e < dim * dim; ++e) { flat[2 * e] = op.mat[e].real(); flat[2 * e + 1] = op.mat[e].imag(); }
-  double* d_mat = nullptr;
-  QS_CUDA(cudaMallocAsync(&d_mat, bytes, stream));
-  QS_CUDA(cudaMemcpyAsync(d_mat, flat.data(), bytes, cudaMemcpyHostToDevice, stream));
-  QS_CUDA(cudaStreamSynchronize(stream));     // flat goes out of scope; generic path is not the fast path
-  BitList bl;
-  for (int f = 0; f < op.k; ++f) bl.bits[f] = op.bits[f];
-  const uint64_t count = 1ull << n;
-  k_generic<<<stream_grid(ctx, count, 256), 256, 0, stream>>>(state, scratch, d_mat, bl, op.k, count);
+// =====================================================================================
+// Dense k-qubit block, 5 <= k <= 10 (Gate.apply with any k, DV/gates.py:44-54): in place,
+// one pass over the state, FP64 tensor-core MMA (DMMA.8x8x4)
+// =====================================================================================
+// A tile is the 2^k amplitudes of the gate's qubits times 8 "columns" (the three lowest
+// index bits the gate does not touch, so rows of 8 amplitudes are 128 contiguous bytes
+// whenever the gate leaves bits 0..2 alone).  With the complex matrix split into real and
+// imaginary parts the update is the real GEMM
+//     out_re = Mr in_re - Mi in_im,   out_im = Mr in_im + Mi in_re        (2^k x 2^k) x (2^k x 8)
+// i.e. four m8n8k4 MMAs per 8-row block and 4-column chunk of M.  The whole tile is staged in
+// shared memory first, every warp keeps its 8x8 output block in registers and writes it
+// straight back to the addresses it came from: no scratch buffer, no second pass.
+struct DenseGeom {
+  int k, ncol, T;
+  uint8_t gate_bits[10];     // index bit of matrix factor f (f = 0: most significant bit of the row index)
+  uint8_t col_bits[3];       // ascending
+  uint8_t tile_bits[16];     // ascending union of the two
+};
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint64_t dense_index(const DenseGeom& G, uint64_t base, int row, int col) {
+  uint64_t idx = base;
+  for (int f = 0; f < G.k; ++f) idx |= (uint64_t)((row >> (G.k - 1 - f)) & 1) << G.gate_bits[f];
+  for (int b = 0; b < G.ncol; ++b) idx |= (uint64_t)((col >> b) & 1) << G.col_bits[b];
+  return idx;
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_block(qs_c128* state, const double* __restrict__ mat, const __grid_constant__ DenseGeom G, uint64_t ntiles) {
+  extern __shared__ __align__(16) unsigned char qs_dense_smem[];
+  qs_c128* tile = reinterpret_cast<qs_c128*>(qs_dense_smem);   // slot of (c, col): c * 8 + (col ^ ((c & 3) << 1))
+  const int k = G.k, dim = 1 << k, ncols = 1 << G.ncol;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x >> 5;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint64_t base = t;
+    for (int l = 0; l < G.T; ++l) {
+      const uint32_t pos = G.tile_bits[l];
+      const uint64_t low = base & ((1ull << pos) - 1ull);
+      base = ((base >> pos) << (pos + 1)) | low;
+    }
+    for (int e = tid; e < dim * 8; e += (int)blockDim.x) {
+      const int c = e >> 3, col = e & 7;
+      qs_c128 v; v.x = 0.0; v.y = 0.0;
+      if (col < ncols) v = state[dense_index(G, base, c, col)];
+      tile[c * 8 + (col ^ ((c & 3) << 1))] = v;
+    }
+    __syncthreads();
+    for (int rb = warp; rb < dim / 8; rb += nwarps) {
+      double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+      const int row = rb * 8 + (lane >> 2);
+      const double2* mrow = reinterpret_cast<const double2*>(mat) + ((size_t)row << k);
+      const int colb = lane >> 2;
+#pragma unroll 4
+      for (int chunk = 0; chunk < dim / 4; ++chunk) {
+        const int c = chunk * 4 + (lane & 3);
+        const double2 mv = __ldg(mrow + c);                              // M[row][c]
+        const qs_c128 b = tile[c * 8 + (colb ^ ((c & 3) << 1))];        // in[c][colb]
+        dmma_8x8x4(re0, re1, mv.x, b.x);
+        dmma_8x8x4(re0, re1, -mv.y, b.y);
+        dmma_8x8x4(im0, im1, mv.x, b.y);
+        dmma_8x8x4(im0, im1, mv.y, b.x);
+      }
+      const int col0 = 2 * (lane & 3);
+      if (col0 < ncols) {
+        qs_c128 o; o.x = re0; o.y = im0;
+        state[dense_index(G, base, row, col0)] = o;
+      }
+      if (col0 + 1 < ncols) {
+        qs_c128 o; o.x = re1; o.y = im1;
+        state[dense_index(G, base, row, col0 + 1)] = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+std::mutex g_dense_upload_lock;
+
+int run_dense_block(DevCtx* ctx, const qs::PlanItem& it, qs_c128* state, int n, int device, cudaStream_t stream) {
+  const qs::Op& op = it.op;
+  const int k = op.k, dim = 1 << k;
+  if (k < 5 || k > 10 || k > n) return qs::fail(QSIM_ERR_UNSUPPORTED, "dense block: k must be in [5, min(10, n)]");
+  {
+    // the matrix goes to the device once per plan (synchronously, like compiling the plan);
+    // executions after the first launch without any host synchronisation
+    std::lock_guard<std::mutex> guard(g_dense_upload_lock);
+    if (!it.dev_mat || it.dev_index != device) {
+      std::vector<double> flat(2 * (size_t)dim * dim);
+      for (int e = 0; e < dim * dim; ++e) { flat[2 * e] = op.mat[e].real(); flat[2 * e + 1] = op.mat[e].imag(); }
+      void* d = nullptr;
+      QS_CUDA(cudaMalloc(&d, sizeof(double) * flat.size()));
+      it.dev_mat = std::shared_ptr<void>(d, [](void* p) { cudaFree(p); });
+      it.dev_index = device;
+      QS_CUDA(cudaMemcpy(d, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  DenseGeom G;
+  memset(&G, 0, sizeof(G));
+  G.k = k;
+  uint64_t gmask = 0;
+  for (int f = 0; f < k; ++f) { G.gate_bits[f] = (uint8_t)op.bits[f]; gmask |= 1ull << op.bits[f]; }
+  for (int b = 0; b < n && G.ncol < 3; ++b)
+    if (!(gmask >> b & 1)) G.col_bits[G.ncol++] = (uint8_t)b;
+  uint64_t tmask = gmask;
+  for (int i = 0; i < G.ncol; ++i) tmask |= 1ull << G.col_bits[i];
+  for (int b = 0; b < n; ++b)
+    if (tmask >> b & 1) G.tile_bits[G.T++] = (uint8_t)b;
+  const uint64_t ntiles = 1ull << (n - G.T);
+  const int smem = (int)sizeof(qs_c128) * dim * 8;
+  const int threads = dim / 8 >= 8 ? 256 : 32 * (dim / 8);
+  if (smem > 48 * 1024) QS_CUDA(cudaFuncSetAttribute(k_dense_block, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dense_block, threads, smem));
+  if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "dense block does not fit on an SM");
+  uint64_t grid = (uint64_t)ctx->sms * (uint64_t)occ;
+  if (grid > ntiles) grid = ntiles;
+  k_dense_block<<<(unsigned)grid, threads, smem, stream>>>(state, (const double*)it.dev_mat.get(), G, ntiles);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
-  QS_CUDA(cudaMemcpyAsync(state, scratch, sizeof(qs_c128) * count, cudaMemcpyDeviceToDevice, stream));
-  QS_CUDA(cudaFreeAsync(d_mat, stream));
   return QSIM_OK;
 }
 
 int execute_plan(const qsim_plan* p, void* state, int n, void* scratch, void* stream) {
   if (!p || !state) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: null argument");
   if (n != p->n) return qs::fail(QSIM_ERR_ARG, "qsim_plan_execute: plan was compiled for a different qubit count");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(state, &ctx);
+  Bound bound;
+  int rc = bind_device(state, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   for (const qs::PlanItem& it : p->items) {
-    rc = it.generic ? run_generic(ctx, it.op, (qs_c128*)state, (qs_c128*)scratch, n, st)
+    rc = it.generic ? run_dense_block(ctx, it, (qs_c128*)state, n, bound.device, st)
                     : launch_pass(ctx, it.pass, (qs_c128*)state, n, st);
     if (rc != QSIM_OK) return rc;
   }
@@ -574,8 +816,9 @@ int qsim_apply_superop(void* vec_rho, int n_qubits, const int* targets, int k, c
 
 int qsim_init_product(void* state, int n_qubits, const double* amps, void* stream) {
   if (!state || !amps || n_qubits < 1 || n_qubits > 40) return qs::fail(QSIM_ERR_ARG, "qsim_init_product: bad argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(state, &ctx);
+  Bound bound;
+  int rc = bind_device(state, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   ProductAmps pa;
@@ -598,8 +841,9 @@ int qsim_measure_probs(const void* state, int n_qubits, int qubit, const double*
                        double* out_norm2, void* stream) {
   if (!state || !bra0 || !bra1 || !out_norm2) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: null argument");
   if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_measure_probs: qubit out of range");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(state, &ctx);
+  Bound bound;
+  int rc = bind_device(state, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnMeasure f;
   f.a = (const qs_c128*)state;
@@ -612,8 +856,9 @@ int qsim_measure_probs(const void* state, int n_qubits, int qubit, const double*
 int qsim_collapse(const void* in, void* out, int n_qubits, int qubit, const double* bra, double norm, void* stream) {
   if (!in || !out || !bra) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: null argument");
   if (n_qubits < 1 || qubit < 0 || qubit >= n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_collapse: qubit out of range");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(in, &ctx);
+  Bound bound;
+  int rc = bind_device(in, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   BraPair b;
   memcpy(b.b, bra, sizeof(b.b));
@@ -628,8 +873,9 @@ int qsim_collapse(const void* in, void* out, int n_qubits, int qubit, const doub
 int qsim_insert(const void* in, void* out, int n_qubits, int position, const double* amp, void* stream) {
   if (!in || !out || !amp) return qs::fail(QSIM_ERR_ARG, "qsim_insert: null argument");
   if (n_qubits < 0 || position < 0 || position > n_qubits) return qs::fail(QSIM_ERR_ARG, "qsim_insert: position out of range");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(in, &ctx);
+  Bound bound;
+  int rc = bind_device(in, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   BraPair a;
   memcpy(a.b, amp, sizeof(a.b));
@@ -644,8 +890,9 @@ int qsim_insert(const void* in, void* out, int n_qubits, int position, const dou
 
 int qsim_reduce_norm2(const void* state, uint64_t n_amps, double* out, void* stream) {
   if (!state || !out) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_norm2: null argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(state, &ctx);
+  Bound bound;
+  int rc = bind_device(state, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnNorm2 f{(const qs_c128*)state};
   double r[2];
@@ -656,8 +903,9 @@ int qsim_reduce_norm2(const void* state, uint64_t n_amps, double* out, void* str
 
 int qsim_reduce_inner(const void* a, const void* b, uint64_t n_amps, double* out_re_im, void* stream) {
   if (!a || !b || !out_re_im) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_inner: null argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(a, &ctx);
+  Bound bound;
+  int rc = bind_device(a, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnInner f{(const qs_c128*)a, (const qs_c128*)b};
   return reduce_to_host(ctx, f, n_amps, out_re_im, (cudaStream_t)stream);
@@ -665,8 +913,9 @@ int qsim_reduce_inner(const void* a, const void* b, uint64_t n_amps, double* out
 
 int qsim_reduce_expect(const void* ket, const void* rho, int n_qubits, double* out_re_im, void* stream) {
   if (!ket || !rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_expect: bad argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(rho, &ctx);
+  Bound bound;
+  int rc = bind_device(rho, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnExpect f{(const qs_c128*)ket, (const qs_c128*)rho, n_qubits};
   return reduce_to_host(ctx, f, 1ull << (2 * n_qubits), out_re_im, (cudaStream_t)stream);
@@ -674,8 +923,9 @@ int qsim_reduce_expect(const void* ket, const void* rho, int n_qubits, double* o
 
 int qsim_reduce_purity(const void* rho, int n_qubits, double* out_re_im, void* stream) {
   if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_purity: bad argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(rho, &ctx);
+  Bound bound;
+  int rc = bind_device(rho, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnPurity f{(const qs_c128*)rho, n_qubits};
   return reduce_to_host(ctx, f, 1ull << (2 * n_qubits), out_re_im, (cudaStream_t)stream);
@@ -683,8 +933,9 @@ int qsim_reduce_purity(const void* rho, int n_qubits, double* out_re_im, void* s
 
 int qsim_reduce_trace(const void* rho, int n_qubits, double* out_re_im, void* stream) {
   if (!rho || !out_re_im || n_qubits < 0 || n_qubits > 20) return qs::fail(QSIM_ERR_ARG, "qsim_reduce_trace: bad argument");
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(rho, &ctx);
+  Bound bound;
+  int rc = bind_device(rho, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   FnTrace f{(const qs_c128*)rho, n_qubits};
   return reduce_to_host(ctx, f, 1ull << n_qubits, out_re_im, (cudaStream_t)stream);
@@ -698,8 +949,9 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
   if (nq < 1 || nq > 2) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_rb_batch: nq must be 1 or 2");
   if (n_seq < 0 || n_opcodes < 1 || n_opcodes > 65536) return qs::fail(QSIM_ERR_ARG, "qsim_rb_batch: bad sizes");
   if (n_seq == 0) return QSIM_OK;
-  DevCtx* ctx = nullptr;
-  int rc = bind_device(out_fidelity, &ctx);
+  Bound bound;
+  int rc = bind_device(out_fidelity, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   const unsigned blocks = (unsigned)((n_seq + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
@@ -744,8 +996,9 @@ int qsim_swap_pack(const void* shard, void* sendbuf, int n_local, int nbits, con
   QsBitSel sel;
   int rc = swap_select("qsim_swap_pack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
   if (rc != QSIM_OK) return rc;
-  DevCtx* ctx = nullptr;
-  rc = bind_device(shard, &ctx);
+  Bound bound;
+  rc = bind_device(shard, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   if (count == 0) return QSIM_OK;
   k_swap_pack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -761,8 +1014,9 @@ int qsim_swap_unpack(void* shard, const void* recvbuf, int n_local, int nbits, c
   QsBitSel sel;
   int rc = swap_select("qsim_swap_unpack", n_local, nbits, local_qubits, bit_values, first, count, &sel);
   if (rc != QSIM_OK) return rc;
-  DevCtx* ctx = nullptr;
-  rc = bind_device(shard, &ctx);
+  Bound bound;
+  rc = bind_device(shard, &bound);
+  DevCtx* ctx = bound.ctx;
   if (rc != QSIM_OK) return rc;
   if (count == 0) return QSIM_OK;
   k_swap_unpack<<<stream_grid(ctx, count, 256), 256, 0, (cudaStream_t)stream>>>(

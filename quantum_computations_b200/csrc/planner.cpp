@@ -10,6 +10,7 @@
 //   * non-diagonal gates need their qubits inside the tile, so each pass picks
 //     the T tile bits that let it absorb the most pending gates.
 #include "planner.h"
+#include "tile_exec.h"
 
 #include <algorithm>
 #include <cstring>
@@ -34,6 +35,8 @@ qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   if (o.max_dense_ops <= 0) o.max_dense_ops = 20;
   if (o.lookahead <= 0) o.lookahead = 600;
   if (o.merge_1q <= 0) o.merge_1q = 1;
+  if (o.max_layers <= 0) o.max_layers = 4;
+  if (o.max_layers > 8) o.max_layers = 8;
   if (o.defer_tail != 1 || o.merge_1q != 1) o.defer_tail = 0;
   if (o.tile_bits > QS_MAX_T) o.tile_bits = QS_MAX_T;
   if (o.max_group > QS_MAX_R) o.max_group = QS_MAX_R;
@@ -288,25 +291,64 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector
 
 namespace {
 
-// shape of a 2x2 matrix: lets the kernel skip the multiplications by exact zeros
-uint8_t mat_form(const Op& op) {
-  if (op.rot) return QS_FORM_ROT;
-  auto zero = [](const cplx& v) { return v.real() == 0.0 && v.imag() == 0.0; };
-  if (zero(op.mat[1]) && zero(op.mat[2])) return QS_FORM_DIAG;
-  if (zero(op.mat[0]) && zero(op.mat[3])) return QS_FORM_ANTIDIAG;
-  return QS_FORM_GENERAL;
+constexpr int kMaxLayerPairs = 96;    // sign pairs attached to one layer
+constexpr int kMaxLo = 48;            // of which (local, outer) pairs
+constexpr int kMaxStepLayers = 8;     // hard cap on layers per step (options.max_layers <= this)
+
+// A layer / step while the walk is still adding gates to them.
+struct WLayer {
+  uint8_t kind = QS_LAYER_ROT;
+  uint8_t form[QS_MAX_R] = {0, 0, 0, 0};
+  double coef[QS_MAX_R][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // (u, t) for TAN, (p, q) for SHEAR3
+  cplx ph[QS_MAX_R][2];                         // phases (and scale) on the factor's 0 / 1 amplitudes
+  bool has_ph = false;
+  int op_idx[QS_MAX_R] = {-1, -1, -1, -1};      // QS_FORM_FULL members / [0]: the dense op
+  int npairs = 0, nlo = 0;
+  uint8_t pairs[kMaxLayerPairs][2];             // global bits, a <= b (a == b: a Z)
+};
+struct WStep {
+  int r = 0;
+  int bits[QS_MAX_R] = {0, 0, 0, 0};            // global bit of factor f
+  bool dense = false;
+  int nlayers = 0;
+  int layers[kMaxStepLayers];
+};
+
+// How a single-qubit op enters a layer.
+struct OneQ {
+  uint8_t form = QS_FORM_NONE;
+  double c0 = 0.0, c1 = 0.0;                    // (u, t) for TAN, (p, q) for SHEAR3
+  cplx ph0 = cplx(1.0, 0.0), ph1 = cplx(1.0, 0.0);
+  bool full = false;                            // needs a QS_LAYER_GENERAL layer
+};
+
+// [[c, -s], [s, c]] . diag(r0, r1) with c, s >= 0, c^2 + s^2 = 1 (plan.h)
+OneQ rotation_form(double c, double s, cplx r0, cplx r1) {
+  OneQ q;
+  if (c >= s) {
+    const double t = s / c, d = 1.0 + t * t;
+    q.form = QS_FORM_TAN; q.c0 = t / d; q.c1 = t;
+    q.ph0 = c * r0; q.ph1 = (c * d) * r1;
+  } else {
+    q.form = QS_FORM_SHEAR3; q.c0 = s / (1.0 + c); q.c1 = s;
+    q.ph0 = r0; q.ph1 = r1;
+  }
+  return q;
 }
 
-// 8-double coefficient slot of one member of a 1Q step
-void write_1q_slot(double* dst, const Op& op) {
-  if (op.rot) {
-    dst[0] = op.c; dst[1] = op.s;
-    dst[2] = op.r0.real(); dst[3] = op.r0.imag();
-    dst[4] = op.r1.real(); dst[5] = op.r1.imag();
-    dst[6] = dst[7] = 0.0;
+OneQ classify_1q(const Op& op) {
+  auto zero = [](const cplx& v) { return v.real() == 0.0 && v.imag() == 0.0; };
+  if (op.rot) return rotation_form(op.c, op.s, op.r0, op.r1);
+  OneQ q;
+  if (zero(op.mat[1]) && zero(op.mat[2])) {
+    q.form = QS_FORM_NONE; q.ph0 = op.mat[0]; q.ph1 = op.mat[3];           // diagonal: phases only
+  } else if (zero(op.mat[0]) && zero(op.mat[3])) {
+    // [[0, b], [c, 0]] = [[0, -1], [1, 0]] . diag(c, -b): a quarter turn
+    q = rotation_form(0.0, 1.0, op.mat[2], -op.mat[1]);
   } else {
-    for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+    q.form = QS_FORM_FULL; q.full = true;
   }
+  return q;
 }
 
 struct Walker {
@@ -320,40 +362,40 @@ struct Walker {
   // tile is the bit set S.  With `pass` == nullptr only the score is computed
   // (and at most opt.lookahead pending ops are visited).
   // Returns dense_taken * 4096 + min(sign_taken, 4095).
+  //
+  // Positions inside a pass are (step, layer) pairs, ordered lexicographically and
+  // encoded as step * 64 + layer.
   long walk(size_t first, uint64_t S, QsPass* pass, std::vector<size_t>* taken_idx) const {
     const uint64_t all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
     uint64_t blocked_full = 0, blocked_diag = 0;
     int dense_taken = 0, sign_taken = 0, visited = 0;
+    const int max_layers = std::min(opt.max_layers, kMaxStepLayers);
 
     int lpos[64];
     {
       int t = 0;
       for (int b = 0; b < n; ++b) lpos[b] = (S >> b & 1) ? t++ : -1;
+      for (int b = n; b < 64; ++b) lpos[b] = -1;
     }
 
-    int nsteps = 0, ncoef = 0, npairs = 0;
-    // Earliest-fit packing of single-qubit gates into 1Q steps: a gate on bit c may
-    // join any existing step after the last matrix on c and not before the step
-    // whose sign block holds the last CZ/Z on c (it commutes with everything else).
-    int step_r[QS_MAX_STEPS];                // members of a 1Q step; -1 = dense step (closed)
+    WStep steps[QS_MAX_STEPS];
+    WLayer layers[QS_MAX_LAYERS];
+    int nsteps = 0, nlayers = 0, ncoef = 0, total_lo = 0;
+    // one layer is held back for the final sign layer
+    const int layer_cap = QS_MAX_LAYERS - 1;
+    const int coef_cap = QS_MAX_COEF - 2 * (1 << QS_MAX_R);      // ... and room for its phase table
     int last_dense[64], last_sign[64];
     for (int b = 0; b < 64; ++b) { last_dense[b] = -1; last_sign[b] = 0; }
-    // Sign pairs taken but not yet attached: each waits for the first later step
-    // whose group contains one of its bits, else for the pass's final block.
+    // Sign pairs taken but not yet attached: each waits for the first later layer
+    // whose group contains one of its bits, else for the pass's final layer.
     uint64_t pend_mask = 0;
     uint8_t pend[256][2];
     int npend = 0;
 
-    // (local position, outer bit) pairs per step; flattened into QsPass::pairs at the end
-    constexpr int kMaxLo = 24;
-    uint8_t step_lo[QS_MAX_STEPS][kMaxLo][2];
-    int step_nlo[QS_MAX_STEPS];
-    int total_lo = 0;
-
-    // Earliest existing step that a matrix on bit c may join, given the pending
-    // pairs that touch c (they would be attached to that step's sign block, so the
-    // step must come after every earlier matrix on their partner bits).
-    auto earliest_step = [&](int c) {
+    // Earliest position that a matrix on bit c may take, given the pending pairs that
+    // touch c (they would be attached to that layer's sign block, so the layer must come
+    // after every earlier matrix on their partner bits).
+    auto earliest_pos = [&](int c) {
       int e = std::max(last_dense[c] + 1, last_sign[c]);
       if (pend_mask >> c & 1)
         for (int p = 0; p < npend; ++p) {
@@ -363,19 +405,22 @@ struct Walker {
         }
       return e;
     };
-    auto pending_lo_count = [&](int c) {
+    auto pending_count = [&](int c, int* lo) {
       int cnt = 0;
+      *lo = 0;
       if (pend_mask >> c & 1)
         for (int p = 0; p < npend; ++p) {
           const int a = pend[p][0], b = pend[p][1];
-          if ((a == c) != (b == c) && lpos[a == c ? b : a] < 0) ++cnt;
+          if (a != c && b != c) continue;
+          ++cnt;
+          if (a != b && lpos[a == c ? b : a] < 0) ++*lo;
         }
       return cnt;
     };
-    // Move every pending pair that touches bit c (factor f of step sidx) into that
-    // step's sign block.
-    auto attach = [&](int c, int sidx, int f, QsStep* st) {
+    // Move every pending pair that touches bit c into layer `li` (position `pos`).
+    auto attach = [&](int c, int li, int pos) {
       if (!(pend_mask >> c & 1)) return;
+      WLayer& L = layers[li];
       int kept = 0;
       uint64_t new_mask = 0;
       for (int p = 0; p < npend; ++p) {
@@ -386,27 +431,26 @@ struct Walker {
           continue;
         }
         const int e = (a == c) ? b : a;              // partner (== c for a Z)
-        last_sign[c] = std::max(last_sign[c], sidx);
-        last_sign[e] = std::max(last_sign[e], sidx);
-        if (e != c && lpos[e] < 0) {
-          step_lo[sidx][step_nlo[sidx]][0] = (uint8_t)lpos[c];
-          step_lo[sidx][step_nlo[sidx]][1] = (uint8_t)e;
-          step_nlo[sidx]++;
-          ++total_lo;
-        }
-        if (!st) continue;
-        st->has_sign = 1;
-        if (e == c) {
-          st->zconst ^= (uint16_t)(1u << lpos[c]);
-        } else if (lpos[e] >= 0) {
-          st->ng[f] ^= (uint16_t)(1u << lpos[e]);
-          // partner inside the same group (multi-qubit dense step): keep ng symmetric
-          for (int f2 = 0; f2 < st->r; ++f2)
-            if (f2 != f && st->gpos[f2] == lpos[e]) st->ng[f2] ^= (uint16_t)(1u << lpos[c]);
-        }
+        last_sign[c] = std::max(last_sign[c], pos);
+        last_sign[e] = std::max(last_sign[e], pos);
+        L.pairs[L.npairs][0] = (uint8_t)a;
+        L.pairs[L.npairs][1] = (uint8_t)b;
+        L.npairs++;
+        if (e != c && lpos[e] < 0) { L.nlo++; ++total_lo; }
       }
       npend = kept;
       pend_mask = new_mask;
+    };
+    auto layer_coef_need = [&](bool full) {
+      return (full ? 8 * opt.max_group : 2 * opt.max_group) + 2 * (1 << opt.max_group);
+    };
+    auto new_layer = [&](int sidx, uint8_t kind) {
+      WLayer& L = layers[nlayers];
+      L = WLayer();
+      L.kind = kind;
+      for (int f = 0; f < QS_MAX_R; ++f) { L.ph[f][0] = cplx(1.0, 0.0); L.ph[f][1] = cplx(1.0, 0.0); }
+      steps[sidx].layers[steps[sidx].nlayers++] = nlayers;
+      return nlayers++;
     };
 
     for (size_t i = first; i < ops.size(); ++i) {
@@ -435,158 +479,285 @@ struct Walker {
         } else {
           blocked_diag |= m;
         }
-      } else {
-        const bool in_tile = (m & ~S) == 0;
-        const bool free_bits = (m & blocked_full) == 0 && (op.diag || (m & blocked_diag) == 0);
-        bool take = in_tile && free_bits && op.k <= QS_MAX_R && dense_taken < opt.max_dense_ops;
-        int join = -1;
-        if (take) {
-          if (op.k == 1) {
-            const int c = op.bits[0];
-            const int nlo = pending_lo_count(c);
-            for (int sidx = earliest_step(c); sidx < nsteps; ++sidx)
-              if (step_r[sidx] >= 1 && step_r[sidx] < opt.max_group && step_nlo[sidx] + nlo <= kMaxLo) {
-                join = sidx;
-                break;
-              }
-          }
-          if (join < 0) {
-            const int need = (op.k == 1) ? 8 * opt.max_group + 2 * (1 << opt.max_group)
-                                         : 2 * (1 << op.k) * (1 << op.k);
-            int nlo = 0;
-            for (int b : op.bits) nlo += pending_lo_count(b);
-            if (nsteps >= QS_MAX_STEPS || ncoef + need > QS_MAX_COEF || nlo > kMaxLo ||
-                total_lo + nlo + npend > QS_MAX_PAIRS)
-              take = false;
+        if ((blocked_full & all) == all) break;
+        continue;
+      }
+      const bool in_tile = (m & ~S) == 0;
+      const bool free_bits = (m & blocked_full) == 0 && (op.diag || (m & blocked_diag) == 0);
+      bool take = in_tile && free_bits && op.k <= QS_MAX_R && dense_taken < opt.max_dense_ops;
+      if (take && op.k == 1) {
+        const int c = op.bits[0];
+        const OneQ q = classify_1q(op);
+        const uint8_t want = q.full ? QS_LAYER_GENERAL : QS_LAYER_ROT;
+        int nlo = 0;
+        const int cnt = pending_count(c, &nlo);
+        const int e = earliest_pos(c);
+        int js = -1, jl = -1;             // chosen step / layer-in-step
+        bool fresh_layer = false;
+        // earliest fit: a round trip costs about four layers, and an early position keeps the
+        // qubit (and its CZ partners) free for what follows
+        for (int sidx = e >> 6; sidx < nsteps && js < 0; ++sidx) {
+          const WStep& st = steps[sidx];
+          if (st.dense) continue;
+          bool member = false;
+          for (int f = 0; f < st.r; ++f) member |= st.bits[f] == c;
+          if (!member && st.r >= opt.max_group) continue;
+          for (int l = (sidx == (e >> 6)) ? (e & 63) : 0; l <= st.nlayers; ++l) {
+            if (l < st.nlayers) {
+              const WLayer& L = layers[st.layers[l]];
+              if (L.kind != want) continue;
+              if (L.npairs + cnt > kMaxLayerPairs || L.nlo + nlo > kMaxLo) continue;
+              js = sidx; jl = l;
+              break;
+            }
+            // a new layer at the end of this step
+            if (st.nlayers >= max_layers || nlayers >= layer_cap) break;
+            if (ncoef + layer_coef_need(q.full) > coef_cap) break;
+            if (cnt > kMaxLayerPairs || nlo > kMaxLo) break;
+            js = sidx; jl = l; fresh_layer = true;
+            break;
           }
         }
-        if (take && join >= 0) {
-          const int c = op.bits[0];
-          const int f = step_r[join];
-          QsStep* st = pass ? &pass->steps[join] : nullptr;
-          if (st) {
-            st->gpos[f] = (uint8_t)lpos[c];
-            st->form[f] = mat_form(op);
-            write_1q_slot(pass->coef + st->coef_off + 8 * f, op);
-            st->r++;
-          }
-          attach(c, join, f, st);
-          step_r[join]++;
-          last_dense[c] = join;
-        } else if (take) {
-          QsStep* st = pass ? &pass->steps[nsteps] : nullptr;
-          if (st) *st = QsStep{};
-          step_nlo[nsteps] = 0;
-          const int dim = 1 << op.k;
-          if (st) {
-            st->coef_off = (uint16_t)ncoef;
-            st->kind = (op.k == 1) ? QS_STEP_1Q : QS_STEP_DENSE;
-            st->r = (uint8_t)op.k;
-            for (int f = 0; f < op.k; ++f) st->gpos[f] = (uint8_t)lpos[op.bits[f]];
-            if (op.k == 1) st->form[0] = mat_form(op);
-            double* dst = pass->coef + ncoef;
-            if (op.k == 1) write_1q_slot(dst, op);
-            else
-              for (int e = 0; e < dim * dim; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
-          }
-          for (int f = 0; f < op.k; ++f) attach(op.bits[f], nsteps, f, st);
-          if (op.k == 1) {
-            ncoef += 8 * opt.max_group + 2 * (1 << opt.max_group);   // later members + phase table
-            step_r[nsteps] = 1;
+        if (js < 0) {
+          // a new step
+          if (nsteps >= QS_MAX_STEPS || nlayers >= layer_cap || ncoef + layer_coef_need(q.full) > coef_cap ||
+              cnt > kMaxLayerPairs || nlo > kMaxLo || total_lo + nlo + npend > QS_MAX_PAIRS) {
+            take = false;
           } else {
-            ncoef += 2 * dim * dim;
-            step_r[nsteps] = -1;
+            steps[nsteps] = WStep();
+            js = nsteps++;
+            jl = 0;
+            fresh_layer = true;
           }
-          for (int b : op.bits) last_dense[b] = nsteps;
+        }
+        if (take) {
+          WStep& st = steps[js];
+          int li;
+          if (fresh_layer) {
+            li = new_layer(js, want);
+            ncoef += layer_coef_need(q.full);
+          } else {
+            li = st.layers[jl];
+          }
+          int f = -1;
+          for (int g = 0; g < st.r; ++g)
+            if (st.bits[g] == c) f = g;
+          if (f < 0) { f = st.r; st.bits[st.r++] = c; }
+          WLayer& L = layers[li];
+          L.form[f] = q.form;
+          L.coef[f][0] = q.c0;
+          L.coef[f][1] = q.c1;
+          if (q.full) {
+            L.op_idx[f] = (int)i;
+          } else {
+            L.ph[f][0] = q.ph0; L.ph[f][1] = q.ph1;
+            if (q.ph0 != cplx(1.0, 0.0) || q.ph1 != cplx(1.0, 0.0)) L.has_ph = true;
+          }
+          const int pos = js * 64 + jl;
+          attach(c, li, pos);
+          last_dense[c] = pos;
+        }
+      } else if (take) {
+        // dense k >= 2 gate: a step of its own with a single layer
+        const int dim = 1 << op.k;
+        int nlo = 0, cnt = 0;
+        for (int b : op.bits) { int lo1 = 0; cnt += pending_count(b, &lo1); nlo += lo1; }
+        if (nsteps >= QS_MAX_STEPS || nlayers >= layer_cap || ncoef + 2 * dim * dim > coef_cap ||
+            cnt > kMaxLayerPairs || nlo > kMaxLo || total_lo + nlo + npend > QS_MAX_PAIRS) {
+          take = false;
+        } else {
+          steps[nsteps] = WStep();
+          WStep& st = steps[nsteps];
+          st.dense = true;
+          st.r = op.k;
+          for (int f = 0; f < op.k; ++f) st.bits[f] = op.bits[f];
+          const int li = new_layer(nsteps, QS_LAYER_DENSE);
+          layers[li].op_idx[0] = (int)i;
+          ncoef += 2 * dim * dim;
+          const int pos = nsteps * 64;
+          for (int f = 0; f < op.k; ++f) attach(op.bits[f], li, pos);
+          for (int b : op.bits) last_dense[b] = pos;
           ++nsteps;
         }
-        if (take) {
-          ++dense_taken;
-          if (taken_idx) taken_idx->push_back(i);
-        } else if (op.diag) {
-          blocked_diag |= m;
-        } else {
-          blocked_full |= m;
-        }
+      }
+      if (take) {
+        ++dense_taken;
+        if (taken_idx) taken_idx->push_back(i);
+      } else if (op.diag) {
+        blocked_diag |= m;
+      } else {
+        blocked_full |= m;
       }
       if ((blocked_full & all) == all) break;
     }
 
-    if (pass) {
-      // phase tables of the steps that hold rotation-form members
-      for (int sidx = 0; sidx < nsteps; ++sidx) {
-        QsStep& st = pass->steps[sidx];
-        if (st.kind != QS_STEP_1Q) continue;
-        bool any = false;
-        for (int f = 0; f < st.r; ++f) any |= st.form[f] == QS_FORM_ROT;
-        if (!any) continue;
-        st.has_phase = 1;
-        st.ph_off = (uint16_t)(st.coef_off + 8 * opt.max_group);
-        for (int m = 0; m < (1 << st.r); ++m) {
-          cplx ph(1.0, 0.0);
-          for (int f = 0; f < st.r; ++f) {
-            if (st.form[f] != QS_FORM_ROT) continue;
-            const double* slot = pass->coef + st.coef_off + 8 * f;
-            const int bit = (m >> (st.r - 1 - f)) & 1;
-            ph *= cplx(slot[2 + 2 * bit], slot[3 + 2 * bit]);
-          }
-          pass->coef[st.ph_off + 2 * m] = ph.real();
-          pass->coef[st.ph_off + 2 * m + 1] = ph.imag();
-        }
-      }
-      // flatten the per-step (local, outer) pair lists
-      for (int sidx = 0; sidx < nsteps; ++sidx) {
-        QsStep& st = pass->steps[sidx];
-        st.pair_off = (uint16_t)npairs;
-        st.n_lo = (uint16_t)step_nlo[sidx];
-        for (int q = 0; q < step_nlo[sidx]; ++q) {
-          pass->pairs[2 * npairs] = step_lo[sidx][q][0];
-          pass->pairs[2 * npairs + 1] = step_lo[sidx][q][1];
-          ++npairs;
-        }
-      }
-      // whatever is still pending goes into the final block
-      uint8_t* dst = pass->pairs + 2 * npairs;
-      int w = 0, n_oo = 0, n_lo = 0;
-      for (int p = 0; p < npend; ++p) {
-        const int a = pend[p][0], b = pend[p][1];
-        if (lpos[a] < 0 && lpos[b] < 0) { dst[w++] = (uint8_t)a; dst[w++] = (uint8_t)b; ++n_oo; }
-      }
-      for (int p = 0; p < npend; ++p) {
-        const int a = pend[p][0], b = pend[p][1];
-        if ((lpos[a] >= 0) != (lpos[b] >= 0)) {
-          const int in = lpos[a] >= 0 ? a : b, outb = lpos[a] >= 0 ? b : a;
-          dst[w++] = (uint8_t)lpos[in]; dst[w++] = (uint8_t)outb; ++n_lo;
-        }
-      }
-      for (int p = 0; p < npend; ++p) {
-        const int a = pend[p][0], b = pend[p][1];
-        if (lpos[a] >= 0 && lpos[b] >= 0) {
-          if (a == b) {
-            pass->fin_zconst ^= (uint16_t)(1u << lpos[a]);
-          } else {
-            pass->fin_nsym[lpos[a]] ^= (uint16_t)(1u << lpos[b]);
-            pass->fin_nsym[lpos[b]] ^= (uint16_t)(1u << lpos[a]);
-          }
-        }
-      }
-      pass->fin_has_sign = npend > 0 ? 1 : 0;
-      pass->fin_pair_off = (uint16_t)npairs;
-      pass->fin_n_oo = (uint16_t)n_oo;
-      pass->fin_n_lo = (uint16_t)n_lo;
-      npairs += n_oo + n_lo;
-      pass->nsteps = (uint32_t)nsteps;
-      pass->ncoef = (uint32_t)ncoef;
-      pass->npairs = (uint32_t)npairs;
-    }
+    if (pass) finalize(*pass, S, lpos, steps, nsteps, layers, pend, npend);
     return (long)dense_taken * 4096 + std::min(sign_taken, 4095);
+  }
+
+  // Turn the walk's steps / layers / leftover pairs into the pass descriptor.
+  void finalize(QsPass& P, uint64_t S, const int* lpos, WStep* steps, int nsteps, WLayer* layers,
+                const uint8_t (*pend)[2], int npend) const {
+    int nlayers_used = 0;
+    for (int s = 0; s < nsteps; ++s) nlayers_used += steps[s].nlayers;
+    // leftover pairs: a sign-only final layer at the end of the last step
+    WLayer fin;
+    bool has_final = npend > 0;
+    if (has_final) {
+      if (nsteps == 0) {
+        steps[0] = WStep();
+        steps[0].r = 1;
+        for (int b = n - 1; b >= 0; --b)
+          if (S >> b & 1) { steps[0].bits[0] = b; break; }
+        nsteps = 1;
+      }
+      fin = WLayer();
+      fin.kind = QS_LAYER_ROT;
+      for (int f = 0; f < QS_MAX_R; ++f) { fin.ph[f][0] = cplx(1.0, 0.0); fin.ph[f][1] = cplx(1.0, 0.0); }
+    }
+    P.nsteps = (uint32_t)nsteps;
+    int ncoef = 0, npairs = 0, nl = 0;
+    for (int s = 0; s < nsteps; ++s) {
+      WStep& ws = steps[s];
+      QsStep& st = P.steps[s];
+      st = QsStep{};
+      st.r = (uint8_t)ws.r;
+      st.layer0 = (uint8_t)nl;
+      uint32_t gmask = 0;
+      for (int f = 0; f < ws.r; ++f) {
+        st.gpos[f] = (uint8_t)lpos[ws.bits[f]];
+        gmask |= 1u << st.gpos[f];
+      }
+      const bool last = s == nsteps - 1;
+      const int count = ws.nlayers + ((last && has_final) ? 1 : 0);
+      for (int k = 0; k < count; ++k) {
+        const bool is_fin = k == ws.nlayers;
+        const WLayer& wl = is_fin ? fin : layers[ws.layers[k]];
+        QsLayer& L = P.layers[nl++];
+        L = QsLayer{};
+        L.kind = wl.kind;
+        L.step = (uint8_t)s;
+        const int r = ws.r, na = 1 << r;
+        // coefficients
+        if (wl.kind == QS_LAYER_DENSE) {
+          const Op& op = ops[wl.op_idx[0]];
+          L.coef_off = (uint16_t)ncoef;
+          for (int e = 0; e < na * na; ++e) {
+            P.coef[ncoef++] = op.mat[e].real();
+            P.coef[ncoef++] = op.mat[e].imag();
+          }
+        } else {
+          L.coef_off = (uint16_t)ncoef;
+          for (int f = 0; f < r; ++f) L.form[f] = wl.form[f];
+          if (wl.kind == QS_LAYER_GENERAL) {
+            for (int f = 0; f < r; ++f) {
+              double* dst = P.coef + ncoef + 8 * f;
+              for (int e = 0; e < 8; ++e) dst[e] = 0.0;
+              if (wl.form[f] != QS_FORM_FULL) continue;
+              const Op& op = ops[wl.op_idx[f]];
+              for (int e = 0; e < 4; ++e) { dst[2 * e] = op.mat[e].real(); dst[2 * e + 1] = op.mat[e].imag(); }
+            }
+            ncoef += 8 * r;
+          } else {
+            for (int f = 0; f < r; ++f) { P.coef[ncoef + 2 * f] = wl.coef[f][0]; P.coef[ncoef + 2 * f + 1] = wl.coef[f][1]; }
+            ncoef += 2 * r;
+          }
+        }
+        // sign block
+        L.pair_off = (uint16_t)npairs;
+        bool coupled[QS_MAX_R][QS_MAX_R] = {};
+        auto add_pair = [&](int a, int b) {
+          if (a == b) { L.zconst ^= (uint16_t)(1u << lpos[a]); return; }
+          const int pa = lpos[a], pb = lpos[b];
+          const bool ga = pa >= 0 && (gmask >> pa & 1), gb = pb >= 0 && (gmask >> pb & 1);
+          auto factor_of = [&](int p) { for (int f = 0; f < r; ++f) if (st.gpos[f] == p) return f; return -1; };
+          if (ga && gb) {
+            const int fa = factor_of(pa), fb = factor_of(pb);
+            coupled[fa][fb] ^= true; coupled[fb][fa] ^= true;
+          } else if (ga || gb) {
+            const int pg = ga ? pa : pb, po = ga ? pb : pa, bo = ga ? b : a;
+            if (po >= 0) {
+              L.ng[factor_of(pg)] ^= (uint16_t)(1u << po);
+            } else {
+              P.pairs[2 * npairs] = (uint8_t)pg; P.pairs[2 * npairs + 1] = (uint8_t)bo; ++npairs; L.n_lo++;
+            }
+          } else if (pa >= 0 && pb >= 0) {         // final layer only: no group bit involved
+            P.fin_nsym[pa] ^= (uint16_t)(1u << pb);
+            P.fin_nsym[pb] ^= (uint16_t)(1u << pa);
+          } else {                                  // final layer only: (local, outer); z is kept by position
+            const int pl = pa >= 0 ? pa : pb, bo = pa >= 0 ? b : a;
+            P.pairs[2 * npairs] = (uint8_t)pl; P.pairs[2 * npairs + 1] = (uint8_t)bo; ++npairs; L.n_lo++;
+          }
+        };
+        if (is_fin) {
+          // (outer, outer) pairs first: they only feed the tile-uniform bit g
+          L.flags |= QS_LF_SIGN | QS_LF_FINAL;
+          P.has_final = 1;
+          P.fin_pair_off = (uint16_t)npairs;
+          for (int p = 0; p < npend; ++p) {           // a Z on an outer bit is the pair (a, a)
+            const int a = pend[p][0], b = pend[p][1];
+            if (lpos[a] < 0 && lpos[b] < 0) {
+              P.pairs[2 * npairs] = (uint8_t)a; P.pairs[2 * npairs + 1] = (uint8_t)b; ++npairs; P.fin_n_oo++;
+            }
+          }
+          L.pair_off = (uint16_t)npairs;
+          for (int p = 0; p < npend; ++p) {
+            const int a = pend[p][0], b = pend[p][1];
+            if (lpos[a] < 0 && lpos[b] < 0) continue;
+            add_pair(a, b);
+          }
+        } else {
+          if (wl.npairs > 0) L.flags |= QS_LF_SIGN;
+          for (int p = 0; p < wl.npairs; ++p) add_pair(wl.pairs[p][0], wl.pairs[p][1]);
+        }
+        // sign pairs inside the group depend on m only: fold them into the phase table (into the
+        // columns of a dense matrix; for a final layer behind a dense one, into its rows)
+        uint32_t qg = 0;
+        for (int m = 0; m < na; ++m) {
+          uint32_t q = 0;
+          for (int f = 0; f < r; ++f)
+            for (int f2 = f + 1; f2 < r; ++f2)
+              if (coupled[f][f2] && ((m >> (r - 1 - f)) & 1) && ((m >> (r - 1 - f2)) & 1)) q ^= 1u;
+          qg |= q << m;
+        }
+        if (wl.kind == QS_LAYER_DENSE) {
+          for (int row = 0; row < na; ++row)
+            for (int c = 0; c < na; ++c)
+              if (qg >> c & 1) {
+                P.coef[L.coef_off + 2 * (row * na + c)] *= -1.0;
+                P.coef[L.coef_off + 2 * (row * na + c) + 1] *= -1.0;
+              }
+        } else if (is_fin && ws.nlayers > 0 && layers[ws.layers[ws.nlayers - 1]].kind == QS_LAYER_DENSE) {
+          const QsLayer& D = P.layers[nl - 2];
+          for (int row = 0; row < na; ++row)
+            if (qg >> row & 1)
+              for (int c = 0; c < na; ++c) {
+                P.coef[D.coef_off + 2 * (row * na + c)] *= -1.0;
+                P.coef[D.coef_off + 2 * (row * na + c) + 1] *= -1.0;
+              }
+        } else if (wl.has_ph || qg) {
+          L.flags |= QS_LF_PHASE;
+          L.ph_off = (uint16_t)ncoef;
+          for (int m = 0; m < na; ++m) {
+            cplx ph((qg >> m & 1) ? -1.0 : 1.0, 0.0);
+            for (int f = 0; f < r; ++f) ph *= wl.ph[f][(m >> (r - 1 - f)) & 1];
+            P.coef[ncoef++] = ph.real();
+            P.coef[ncoef++] = ph.imag();
+          }
+        }
+      }
+      st.nlayers = (uint8_t)count;
+    }
+    P.nlayers = (uint32_t)nl;
+    P.ncoef = (uint32_t)ncoef;
+    P.npairs = (uint32_t)npairs;
   }
 };
 
 // Order the free local positions of a step: the three fastest thread bits go to
-// positions that differ mod 3 (conflict-free with the XOR-fold swizzle), lanes 3-4
-// next, then the `nwarp` warp-owned positions (thread-id bits 5..7), then the
-// per-thread iteration bits.
+// positions below 6 that differ mod 3 (conflict-free under the 128-byte swizzle,
+// tile_exec.h), lanes 3-4 next, then the `nwarp` warp-owned positions (thread-id bits
+// 5..7), then the per-thread iteration bits.
 void order_free_positions(QsStep& st, int T, const int* warp_pos, int nwarp) {
   bool used[QS_MAX_T + 1] = {false};
   for (int f = 0; f < st.r; ++f) used[st.gpos[f]] = true;
@@ -597,7 +768,7 @@ void order_free_positions(QsStep& st, int T, const int* warp_pos, int nwarp) {
   std::vector<int> order;
   bool have[3] = {false, false, false};
   for (int p : freep)
-    if (!have[p % 3]) { have[p % 3] = true; order.push_back(p); }
+    if (p < 6 && !have[p % 3]) { have[p % 3] = true; order.push_back(p); }
   for (int p : freep)
     if (std::find(order.begin(), order.end(), p) == order.end()) order.push_back(p);
   if (nwarp > 0) order.insert(order.begin() + 5, warp_pos, warp_pos + nwarp);   // needs >= 5 lane positions
@@ -612,18 +783,63 @@ void order_free_positions(QsStep& st, int T, const int* warp_pos, int nwarp) {
 void assign_runs(QsPass& P) {
   const int T = (int)P.T;
   const int nsteps = (int)P.nsteps;
+  auto group_mask = [&](int i) {
+    uint32_t g = 0;
+    for (int f = 0; f < P.steps[i].r; ++f) g |= 1u << P.steps[i].gpos[f];
+    return g;
+  };
+  // is step i left with three lane positions below 6 with different residues mod 3?
+  auto lanes_ok = [&](int i, uint32_t wmask) {
+    const uint32_t g = group_mask(i) | wmask;
+    int have = 0;
+    for (int p = 0; p < T && p < 6; ++p)
+      if (!(g >> p & 1)) have |= 1 << (p % 3);
+    return have == 7;
+  };
+  // Best warp-owned positions for the run [s, e): QS_WARP_BITS positions that no step of the
+  // run uses as a group bit, chosen to leave as many steps as possible conflict-free
+  // (highest positions first among equals).  Returns the number of conflict-free steps, -1
+  // if there are not enough unused positions.
+  auto best_warp_positions = [&](int s, int e, uint32_t used, int* wp) {
+    int cand[QS_MAX_T], nc = 0;
+    for (int p = T - 1; p >= 0; --p)
+      if (!(used >> p & 1)) cand[nc++] = p;
+    if (nc < QS_WARP_BITS) return -1;
+    if (QS_WARP_BITS != 3) {
+      for (int i = 0; i < QS_WARP_BITS; ++i) wp[i] = cand[i];
+      return 0;
+    }
+    int best = -1;
+    for (int a = 0; a < nc; ++a)
+      for (int b = a + 1; b < nc; ++b)
+        for (int c = b + 1; c < nc; ++c) {
+          const uint32_t wmask = (1u << cand[a]) | (1u << cand[b]) | (1u << cand[c]);
+          int ok = 0;
+          for (int i = s; i < e; ++i) ok += lanes_ok(i, wmask) ? 1 : 0;
+          if (ok > best) { best = ok; wp[0] = cand[a]; wp[1] = cand[b]; wp[2] = cand[c]; }
+        }
+    return best;
+  };
   int s = 0;
   while (s < nsteps) {
+    // Grow the run while warp-owned positions exist that cost no step its conflict-free
+    // thread map: a bank conflict doubles a step's shared-memory time, a block-level
+    // barrier instead of a warp-level one costs far less.
     uint32_t used = 0;
-    int e = s, maxr = 0;
+    int e = s, maxr = 0, can_ok = 0;
+    int wp[4] = {0, 0, 0, 0};
     while (e < nsteps) {
-      uint32_t u = used;
-      const QsStep& st = P.steps[e];
-      for (int f = 0; f < st.r; ++f) u |= 1u << st.gpos[f];
-      const int r = std::max(maxr, (int)st.r);
+      const uint32_t u = used | group_mask(e);
+      const int r = std::max(maxr, (int)P.steps[e].r);
       if (T - __builtin_popcount(u) < QS_WARP_BITS || T - r < QS_THREADS_LOG2) break;
+      int trial[4];
+      const int ok = best_warp_positions(s, e + 1, u, trial);
+      const int want = can_ok + (lanes_ok(e, 0) ? 1 : 0);
+      if (ok < 0 || (e > s && ok < want)) break;
       used = u;
       maxr = r;
+      can_ok = want;
+      for (int i = 0; i < QS_WARP_BITS; ++i) wp[i] = trial[i];
       ++e;
     }
     if (e == s) {                       // no room for warp-owned positions: plain block-synchronised step
@@ -632,52 +848,51 @@ void assign_runs(QsPass& P) {
       ++s;
       continue;
     }
-    // Warp-owned positions: any QS_WARP_BITS positions that no step of the run uses as a
-    // group bit.  Prefer a choice that leaves every step three lane positions with different
-    // residues mod 3 (conflict-free 128-bit accesses under the XOR-fold swizzle, tile_exec.h);
-    // the highest positions otherwise.
-    int wp[4], nw = 0;
-    {
-      int cand[QS_MAX_T], nc = 0;
-      for (int p = T - 1; p >= 0; --p)
-        if (!(used >> p & 1)) cand[nc++] = p;
-      auto steps_ok = [&](uint32_t wmask) {          // steps of the run left conflict-free
-        int ok = 0;
-        for (int i = s; i < e; ++i) {
-          uint32_t g = 0;
-          for (int f = 0; f < P.steps[i].r; ++f) g |= 1u << P.steps[i].gpos[f];
-          int have = 0;
-          for (int p = 0; p < T; ++p)
-            if (!((g | wmask) >> p & 1)) have |= 1 << (p % 3);
-          ok += have == 7;
-        }
-        return ok;
-      };
-      bool found = false;
-      if (QS_WARP_BITS == 3 && nc >= 3) {
-        int best = -1;
-        for (int a = 0; a < nc; ++a)
-          for (int b = a + 1; b < nc; ++b)
-            for (int c = b + 1; c < nc; ++c) {
-              const int ok = steps_ok((1u << cand[a]) | (1u << cand[b]) | (1u << cand[c]));
-              if (ok > best) {                      // candidates come highest positions first
-                best = ok;
-                wp[0] = cand[a]; wp[1] = cand[b]; wp[2] = cand[c];
-                nw = 3;
-                found = true;
-              }
-            }
-      }
-      if (!found) {
-        nw = 0;
-        for (int i = 0; i < nc && nw < QS_WARP_BITS; ++i) wp[nw++] = cand[i];
-      }
+    if (e == s + 1 && !lanes_ok(s, (1u << wp[0]) | (1u << wp[1]) | (1u << wp[2])) && lanes_ok(s, 0)) {
+      // a run of one step gains nothing from warp-owned positions
+      order_free_positions(P.steps[s], T, nullptr, 0);
+      P.steps[s].block_sync = 1;
+      ++s;
+      continue;
     }
     for (int i = s; i < e; ++i) {
       order_free_positions(P.steps[i], T, wp, QS_WARP_BITS);
       P.steps[i].block_sync = (i == e - 1) ? 1 : 0;
     }
     s = e;
+  }
+}
+
+// Thread-independent tables of the steps (they depend on the thread maps chosen by
+// assign_runs): where the amplitudes of a work item and the per-thread iterations sit.
+void finish_tables(QsPass& P) {
+  const int T = (int)P.T;
+  for (uint32_t s = 0; s < P.nsteps; ++s) {
+    QsStep& st = P.steps[s];
+    const int r = st.r;
+    for (int m = 0; m < (1 << QS_MAX_R); ++m) {
+      uint32_t d = 0;
+      if (m < (1 << r))
+        for (int f = 0; f < r; ++f) d |= (uint32_t)((m >> (r - 1 - f)) & 1) << st.gpos[f];
+      st.sdepb[m] = qs_swz(d) << 4;
+    }
+    const int nfree = T - r;
+    const int lo_bits = std::min(nfree, QS_THREADS_LOG2);
+    for (int i = 0; i < QS_MAX_WORK; ++i) {
+      const uint32_t jhi =
+          i < (1 << (nfree - lo_bits)) ? qs_scatter8((uint32_t)i, st.fpos + QS_THREADS_LOG2, nfree - lo_bits) : 0u;
+      st.hi[i] = jhi | (qs_swz(jhi) << 16);
+    }
+  }
+  if (P.has_final) {
+    const QsStep& st = P.steps[P.nsteps - 1];
+    uint32_t qhi = 0;
+    for (int i = 0; i < QS_MAX_WORK; ++i) {
+      const uint32_t jhi = st.hi[i] & 0xffffu;
+      qhi |= qs_fin_quad(P, jhi) << i;
+      P.fin_neigh[i] = (uint16_t)qs_fin_neigh(P, jhi);
+    }
+    P.fin_qhi = (uint16_t)qhi;
   }
 }
 
@@ -764,13 +979,16 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
       return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
     for (size_t idx : taken) done[idx] = 1;
     assign_runs(P);
+    finish_tables(P);
     for (uint32_t s = 0; s < P.nsteps; ++s) {
-      QsStep& st = P.steps[s];
       stats.n_steps++;
-      stats.n_warp_syncs += st.block_sync ? 0 : 1;
-      stats.n_dense += (st.kind == QS_STEP_1Q) ? st.r : 1;
+      stats.n_warp_syncs += P.steps[s].block_sync ? 0 : 1;
     }
-    for (size_t idx : taken) stats.n_sign += ops[idx].kind == OP_SIGN ? 1 : 0;
+    stats.n_layers += P.nlayers;
+    for (size_t idx : taken) {
+      stats.n_sign += ops[idx].kind == OP_SIGN ? 1 : 0;
+      stats.n_dense += ops[idx].kind == OP_DENSE ? 1 : 0;
+    }
     stats.n_passes++;
     out->items.push_back(std::move(it));
   }

@@ -3,6 +3,7 @@
 #pragma once
 #include <complex>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -35,9 +36,13 @@ struct Op {
 };
 
 struct PlanItem {
-  bool generic = false;
+  bool generic = false;      // a dense block on more than QS_MAX_R qubits (own kernel)
   QsPass pass;               // valid when !generic
   Op op;                     // valid when generic
+  // device copy of op.mat, made at the first execution and owned by the plan
+  // (libqsim_b200.so only; the deleter is cudaFree)
+  mutable std::shared_ptr<void> dev_mat;
+  mutable int dev_index = -1;
 };
 
 }  // namespace qs

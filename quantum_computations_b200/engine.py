@@ -27,7 +27,7 @@ if os.environ.get("QSIM_LIB"):          # development: try an experimental build
 
 # Planner knobs (0 = library default); bench.py sweeps these.
 PLAN_OPTIONS = {"tile_bits": 0, "low_bits": 0, "max_group": 0, "max_dense_ops": 0, "lookahead": 0,
-                "merge_1q": 0, "defer_tail": 0, "apply_tail_mask": 0}
+                "merge_1q": 0, "defer_tail": 0, "max_layers": 0, "apply_tail_mask": 0}
 
 
 def _as_c128(arr) -> np.ndarray:
@@ -211,12 +211,10 @@ class Plan:
         return [(q, out[q]) for q in range(self.n_bits) if not np.array_equal(out[q], eye)]
 
     def execute(self, buf, scratch=None) -> None:
+        """Run the plan on ``buf`` in place.  (``scratch`` is accepted for compatibility and
+        unused: gates on more than four qubits run in place as well.)"""
         be = self.backend
-        if self.stats["n_generic"] and scratch is None:
-            scratch = be.empty(1 << self.n_bits)
-        _capi.check(be.lib, be.lib.qsim_plan_execute(
-            self._plan, be.ptr(buf), self.n_bits, be.ptr(scratch) if scratch is not None else None,
-            be.stream()))
+        _capi.check(be.lib, be.lib.qsim_plan_execute(self._plan, be.ptr(buf), self.n_bits, None, be.stream()))
 
     def __del__(self):
         plan, self._plan = getattr(self, "_plan", None), None
