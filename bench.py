@@ -44,6 +44,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC = "gates/sec (30q c128 random circuit, depth 200)"
+METRIC_SHARDED = "gates/sec (34q c128 random circuit, depth 200, sharded over the GPUs)"
+ALT_MAX_DENSE = 8            # matrices per pass of the HBM-roof operating point (roofline_hbm_point)
+PASS_PARAM_BYTES = 28672     # sizeof(QsPass) + tensor map + geometry: kernel parameters per tile-pass launch
 # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
 # `ncu --set full` capture summarised in profiles/r1_ncu_full_k_tile_pass_n30.csv (17.18 GB + 17.12 GB)
 NCU_TRAFFIC_N30 = 34.35e9
@@ -55,7 +58,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--qubits", type=int, default=0, help="0 = 30 on one GPU, 30+log2(N) sharded")
+    ap.add_argument("--qubits", type=int, default=0, help="0 = 30 on one GPU, 34 sharded over N > 1 GPUs")
     ap.add_argument("--depth", type=int, default=200)
     ap.add_argument("--seed", type=int, default=30)
     ap.add_argument("--tile-bits", type=int, default=0)
@@ -65,6 +68,11 @@ def parse_args():
     ap.add_argument("--lookahead", type=int, default=0)
     ap.add_argument("--max-layers", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the HBM-roof operating point")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1-C3 secondary entries")
+    ap.add_argument("--rb-sequences", type=int, default=10000)
+    ap.add_argument("--no-check", action="store_true", help="sharded: skip the circuit-then-inverse check")
+    ap.add_argument("--check-depth", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--traffic-bytes", type=float, default=None,
@@ -155,6 +163,186 @@ def plan_options(args) -> dict:
             "max_dense_ops": args.max_dense, "lookahead": args.lookahead, "max_layers": args.max_layers}
 
 
+# ---- secondary configurations (BASELINE.json configs C1-C3) ---------------------------------------------
+RB_DEPTHS = (8, 10, 15, 20)
+
+
+def rb_circuits(count: int, seed: int = 20251018):
+    from quantum_computations_b200 import workloads
+    rng = np.random.default_rng(seed)
+    return [workloads.rb_random_circuit(2, RB_DEPTHS[i % 4], rng) for i in range(count)]
+
+
+def _rb_cpu_sequence(spec):
+    """One RB sequence by the reference's algorithm (oracle/dense_ref.py): dense operators on the
+    2-qubit density matrix, Kraus sums for the GKP channel.  Returns (fidelity, purity)."""
+    sys.path.insert(0, ROOT)
+    from oracle import dense_ref, gkp_noise
+    from quantum_computations_b200 import channels, gates
+    noise = channels.GKPNoise(10.0)
+    rho = np.zeros((4, 4), dtype=np.complex128)
+    rho[0, 0] = 1.0
+    psi = np.array([1, 0, 0, 0], dtype=np.complex128)
+    for name, idx in spec:
+        g = getattr(gates, name)(*idx)
+        rho = dense_ref.apply_matrix(rho, g.indices, g.matrix)
+        psi = dense_ref.apply_matrix(psi, g.indices, g.matrix)
+        for q, (px, pz) in zip(g.indices, noise.flips_for(g)):
+            rho = dense_ref.apply_kraus(rho, [q], gkp_noise.pauli_flip_kraus(px, pz))
+    return float(dense_ref.fidelity(rho, psi)), float(dense_ref.purity(rho))
+
+
+def _rb_cpu_chunk(specs):
+    return [_rb_cpu_sequence(s) for s in specs]
+
+
+def secondary_rb(sequences: int, cpu_seconds: float, rank: int = 0, world: int = 1, gather=None) -> dict:
+    """C2: `sequences` two-qubit RB sequences (the reference's random_circ generator, depths
+    8/10/15/20) as density matrices with the 10 dB GKP channel after every gate."""
+    import multiprocessing as mp
+    import torch
+    from quantum_computations_b200 import batched, channels
+    t0 = time.perf_counter()
+    circuits = rb_circuits(sequences)
+    gen_s = time.perf_counter() - t0
+    ngates = sum(len(c) for c in circuits)
+    sim = batched.BatchedSimulator(2, channels.GKPNoise(10.0))
+
+    def once():
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = batched.run_replicas(sim, circuits, rank=rank, world=world, gather=gather)
+        torch.cuda.synchronize()
+        return r, time.perf_counter() - t
+
+    res, cold_s = once()                       # first sight of the gate objects: opcodes are worked out
+    res, warm_s = once()
+    res, warm2_s = once()
+    warm_s = min(warm_s, warm2_s)
+    out = {"config": "C2", "workload": f"{sequences} two-qubit RB sequences (depths {list(RB_DEPTHS)}), density "
+                                       "matrix + GKP channel at 10 dB", "gates": ngates,
+           "sequences_per_s": sequences / warm_s, "seconds_e2e": warm_s, "seconds_e2e_first_call": cold_s,
+           "note": "host circuit objects in, fidelity/purity arrays out; the first call also derives the opcode of "
+                   "every gate object, later calls read it back from the objects",
+           "circuit_generation_seconds": gen_s, "n_gpus": world}
+    if rank == 0:
+        specs = [[(type(g).__name__, list(g.indices)) for g in c] for c in circuits]
+        # one process
+        n1, t = 0, time.perf_counter()
+        worst = 0.0
+        while n1 < len(specs) and time.perf_counter() - t < cpu_seconds / 2:
+            f, pu = _rb_cpu_sequence(specs[n1])
+            if world == 1 or gather is not None:
+                worst = max(worst, abs(res["fidelity"][n1] - f), abs(res["purity"][n1] - pu))
+            n1 += 1
+        one = n1 / (time.perf_counter() - t)
+        # multiprocessing.Pool over the host cores (PAPER/average_clifford_fidelity.py:212-214)
+        cores = os.cpu_count() or 1
+        per = max(8, int(one * cpu_seconds / 2))
+        chunks = [specs[(i * per) % len(specs):][:per] for i in range(cores)]
+        try:
+            with mp.get_context("spawn").Pool(cores) as pool:
+                pool.map(_rb_cpu_chunk, [c[:2] for c in chunks])      # start the workers
+                t = time.perf_counter()
+                pool.map(_rb_cpu_chunk, chunks)
+                many = sum(len(c) for c in chunks) / (time.perf_counter() - t)
+        except Exception as exc:                                       # pragma: no cover
+            many = None
+            out["cpu_pool_error"] = repr(exc)
+        out.update({"cpu_port_sequences_per_s_1_process": one, "cpu_port_sequences_per_s_pool": many,
+                    "cpu_cores": cores, "cpu_sample": n1,
+                    "speedup_vs_1_process": sequences / warm_s / one,
+                    "speedup_vs_pool": (sequences / warm_s / many) if many else None,
+                    "max_abs_diff_fidelity_purity_vs_oracle": worst,
+                    "mean_fidelity": float(np.mean(res["fidelity"])), "mean_purity": float(np.mean(res["purity"]))})
+    return out
+
+
+def secondary_grover() -> dict:
+    """C1: the reference's 3-qubit Grover circuit on rho with the GKP channel, checked against
+    vectors produced by the reference itself (tests/golden/noisy_grover.npz)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden.specs import from_spec
+    from quantum_computations_b200 import channels, gates, simulator, states
+    from quantum_computations_b200.simulator import Simulator
+    z = np.load(os.path.join(ROOT, "tests", "golden", "noisy_grover.npz"))
+    meta = json.loads(str(z["meta"]))
+    worst, secs, nops = 0.0, [], 0
+    for rec in meta:
+        circ = [from_spec(s, gates, simulator, z, channels, states) for s in rec["circuit"]]
+        noisy = channels.GKPNoise(rec["db"]).noisy(circ)
+        rho0 = np.zeros((8, 8), dtype=np.complex128)
+        rho0[0, 0] = 1.0
+        sim = Simulator(noisy)
+        sim.run(rho0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = sim.run(rho0)
+        torch.cuda.synchronize()
+        secs.append(time.perf_counter() - t0)
+        worst = max(worst, float(np.abs(got - z[rec["out"]]).max() / np.abs(z[rec["out"]]).max()))
+        nops = len(noisy)
+    return {"config": "C1", "workload": "3-qubit Grover search on rho with the GKP finite-squeezing channel",
+            "runs": len(meta), "ops_per_run": nops, "seconds_per_run": float(np.mean(secs)),
+            "max_rel_err_vs_reference_vectors": worst}
+
+
+def secondary_dm(n: int = 12, depth: int = 100) -> dict:
+    """C3: n-qubit density matrix (2n-bit vec), layered Clifford+T circuit, a GKP channel after
+    every gate; parity of the same generator at n = 6 against the CPU oracle."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden.specs import as_oracle_ops
+    from oracle import strided
+    from quantum_computations_b200 import channels, engine, workloads
+    from quantum_computations_b200.simulator import Simulator
+    from quantum_computations_b200.states import State
+    noise = channels.GKPNoise(10.0)
+    layers = workloads.dm_random_layers(n, depth, 12)
+    circ = noise.noisy([g for layer in layers for g in layer])
+    be = engine.get_backend()
+    ops = []
+    for g in circ:
+        ops.extend(g.lowered(n, True))
+    t0 = time.perf_counter()
+    plan = engine.Plan(be, 2 * n, ops)
+    plan_s = time.perf_counter() - t0
+
+    def fresh():
+        st = engine.DeviceState.product([State.ZERO.get()] * (2 * n), be)
+        st.ndim = 2
+        return st
+
+    state = fresh()
+    plan.execute(state.buf)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(3):
+        state = fresh()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.execute(state.buf)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    # parity at a size the oracle reaches
+    ns = 6
+    small = noise.noisy([g for layer in workloads.dm_random_layers(ns, 20, 12) for g in layer])
+    rho0 = np.zeros((2 ** ns, 2 ** ns), dtype=np.complex128)
+    rho0[0, 0] = 1.0
+    got = Simulator(small).run(rho0)
+    ref, _ = strided.run(as_oracle_ops(small), rho0)
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    passes = plan.stats["n_passes"]
+    return {"config": "C3", "workload": f"{n}-qubit noisy density matrix ({2 * n}-bit vec), Clifford+T depth {depth}, "
+                                        "per-gate GKP channels", "ops_with_channels": len(circ), "plan": plan.stats,
+            "plan_seconds": plan_s, "ms_total": best, "ms_per_pass": best / max(1, passes),
+            "us_per_gate_or_channel": 1e3 * best / len(circ), "trace": float(state.trace().real),
+            "purity": float(state.purity()), "parity_rel_err_vs_oracle_n6": err}
+
+
 # ---- reference arm -----------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -171,22 +359,39 @@ def run_reference(args):
     total = time.perf_counter() - t_all
     value = float(np.mean(vals))
     base["value"] = value
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": args.gpus,
+    metric = METRIC if args.gpus == 1 else METRIC_SHARDED
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": "gates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic",
             "config": {"workload": "C4 generator (sv_random_circuit, depth 200, seed 30) run by the reference's "
-                                   "dense-operator algorithm at N=12; it cannot hold N=30"},
+                                   "dense-operator algorithm at N=12; it cannot hold N=30 or N=34",
+                       "same_config": False},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ---- B200 arm ---------------------------------------------------------------------------------------------
+def time_plan(backend, plan, state, reset, steps: int):
+    """CUDA-event time of `steps` executions of a resident plan (ms, total)."""
+    import torch
+    total = 0.0
+    for _ in range(steps):
+        reset()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        plan.execute(state.buf)
+        ev1.record()
+        torch.cuda.synchronize()
+        total += ev0.elapsed_time(ev1)
+    return total
+
+
 def run_b200(args):
     import torch
-    import torch.distributed as dist
-    from quantum_computations_b200 import engine, workloads
+    from quantum_computations_b200 import _capi, engine, workloads
     from quantum_computations_b200.simulator import Simulator
     from quantum_computations_b200.states import State
 
@@ -215,15 +420,11 @@ def run_b200(args):
     passes = stats["n_passes"]
 
     state = engine.DeviceState.product([State.ZERO.get()] * n, backend)
-    zero_amps = [State.ZERO.get()] * n
+    amps = np.ascontiguousarray(np.stack([np.asarray(State.ZERO.get(), dtype=np.complex128)] * n))
 
     def reset():
-        lib = backend.lib
-        amps = np.ascontiguousarray(np.stack([np.asarray(a, dtype=np.complex128) for a in zero_amps]))
-        from quantum_computations_b200 import _capi
-        _capi.check(lib, lib.qsim_init_product(backend.ptr(state.buf), n,
-                                               amps.view(np.float64).ctypes.data_as(_capi.c_double_p),
-                                               backend.stream()))
+        _capi.check(backend.lib, backend.lib.qsim_init_product(
+            backend.ptr(state.buf), n, amps.view(np.float64).ctypes.data_as(_capi.c_double_p), backend.stream()))
 
     for _ in range(args.warmup):
         reset()
@@ -231,17 +432,8 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     launches0 = engine.launch_count(backend)
-    kernel_ms = 0.0
     with ClockSampler(local_rank) as clocks:
-        for _ in range(args.steps):
-            reset()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            ev0.record()
-            plan.execute(state.buf)
-            ev1.record()
-            torch.cuda.synchronize()
-            kernel_ms += ev0.elapsed_time(ev1)
+        kernel_ms = time_plan(backend, plan, state, reset, args.steps)
     launches = engine.launch_count(backend) - launches0 - args.steps      # minus the reset kernels
     norm = state.norm()
     value = args.steps * ngates / (kernel_ms * 1e-3)
@@ -252,12 +444,33 @@ def run_b200(args):
     launch_ms = kernel_ms / max(1, args.steps * passes)
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = args.traffic_bytes
-    if traffic is None and n == 30 and not any(opts.values()):
+    if traffic is None and n == 30:
         traffic = NCU_TRAFFIC_N30
     roofline = {"bound": "hbm", "kernel": "k_tile_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launches_per_step": passes,
-                "mean_launch_ms": launch_ms}
+                "mean_launch_ms": launch_ms,
+                "operating_point": "default plan: as many gates per HBM pass as the SM absorbs (max gates/s)"}
+
+    # the same circuit planned for the HBM roof instead of for gates/s: fewer gates per pass
+    roofline_hbm_point = None
+    if not args.no_alt and not any(opts.values()):
+        alt_opts = dict(opts, max_dense_ops=ALT_MAX_DENSE)
+        alt = engine.Plan(backend, n, ops, alt_opts)
+        reset()
+        alt.execute(state.buf)
+        alt_ms = time_plan(backend, alt, state, reset, max(1, min(2, args.steps)))
+        alt_steps = max(1, min(2, args.steps))
+        alt_launch = alt_ms / (alt_steps * alt.stats["n_passes"])
+        alt_ach = bytes_per_launch / (alt_launch * 1e-3) / 1e9
+        roofline_hbm_point = {"bound": "hbm", "kernel": "k_tile_pass", "achieved": alt_ach, "peak": peak,
+                              "unit": "GB/s", "frac": alt_ach / peak, "traffic": None,
+                              "plan_options": alt_opts, "launches_per_step": alt.stats["n_passes"],
+                              "mean_launch_ms": alt_launch, "gates_per_s": alt_steps * ngates / (alt_ms * 1e-3),
+                              "final_norm": state.norm(),
+                              "operating_point": f"at most {ALT_MAX_DENSE} matrices per pass: the pass runs near the "
+                                                 "HBM roof, the circuit needs more passes"}
+        del alt
 
     # end to end through the public API, host buffers on both sides
     e2e = None
@@ -278,14 +491,24 @@ def run_b200(args):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / e2e_steps
             assert abs(np.vdot(out[:1 << 20], out[:1 << 20]).real) >= 0.0
-            h2d = passes * 25288 + 64 * n                       # kernel-parameter blocks + product-state amplitudes
+            h2d = passes * PASS_PARAM_BYTES + 64 * n            # kernel-parameter blocks + product-state amplitudes
             e2e = {"value": ngates / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": need,
                    "seconds_per_step": dt, "steps": e2e_steps,
                    "note": "Simulator(circuit).run([ZERO]*n, out=pinned): lowering, plan lookup (the plan compiled "
                            "by the warm-up run is reused through the simulator's content-keyed cache; compiling takes "
                            "config.plan_seconds), product state, all passes, 2^n x 16 B device-to-host copy"}
+            del out, sim
         else:
             e2e = {"value": None, "unit": "gates/s", "skipped": "host memory too small for the 2^n output buffer"}
+    torch.cuda.empty_cache()
+
+    secondary = []
+    if not args.no_secondary:
+        for fn in (secondary_grover, lambda: secondary_rb(args.rb_sequences, args.cpu_seconds), secondary_dm):
+            try:
+                secondary.append(fn())
+            except Exception as exc:                             # a secondary line must not sink the headline
+                secondary.append({"error": repr(exc)})
 
     base = None
     if not args.no_cpu_baseline:
@@ -299,8 +522,8 @@ def run_b200(args):
                                    "exceeds L2, no flush needed",
                        "plan": stats, "plan_options": opts, "plan_seconds": plan_seconds,
                        "gates_per_pass": ngates / max(1, passes), "final_norm": norm},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks.summary()}
+            "roofline": roofline, "roofline_hbm_point": roofline_hbm_point, "cpu_baseline": base, "e2e": e2e,
+            "secondary": secondary, "gpu_launches": int(launches), "clocks": clocks.summary()}
     print(json.dumps(line))
 
 

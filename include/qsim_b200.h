@@ -176,6 +176,24 @@ int qsim_ipc_export(void* ptr, unsigned char* handle64);               /* 64-byt
 int qsim_ipc_import(int device, const unsigned char* handle64, void** out_ptr);
 int qsim_ipc_release(void* imported_ptr);
 int qsim_peer_copy(void* dst, const void* src, uint64_t bytes, void* stream);
+/* CUDA-IPC handle of the allocation that holds `ptr` (any cudaMalloc'ed memory, e.g. a
+ * PyTorch tensor) and the byte offset of `ptr` inside it: the importer adds the offset to
+ * what qsim_ipc_import returns. */
+int qsim_ipc_export_ex(void* ptr, unsigned char* handle64, uint64_t* offset);
+/* The whole k-qubit exchange as ONE kernel over NVLink peer memory (gather + transfer +
+ * scatter fused, in place on both sides, no staging): this rank swaps, with each of the
+ * 2^k - 1 partners, the block of `shard` whose k local qubits spell the partner's rank bits
+ * against the partner's block whose local qubits spell this rank's.  Pattern d (bit i <->
+ * local_qubits[i]) names the partner that differs in those rank bits; peer_shards[d] is
+ * that partner's shard mapped into this process (qsim_ipc_import; entry 0 unused),
+ * partner_is_lower[d] != 0 if the partner's rank number is below this rank's (the two
+ * ranks of a pair split the amplitudes between them by that).  my_bits[i] is this rank's
+ * value of the rank bit traded against local_qubits[i].  The caller must make sure, with
+ * stream-ordered barriers over the ranks, that every rank's earlier work on its shard is
+ * complete before any rank launches, and that every rank's launch is complete before any
+ * rank touches its shard again. */
+int qsim_exchange_p2p(void* shard, void* const* peer_shards, int n_local, int nbits, const int* local_qubits,
+                      const int* my_bits, const int* partner_is_lower, void* stream);
 
 /* Launch statistics since process start (kernels launched by this library). */
 int64_t qsim_launch_count(void);

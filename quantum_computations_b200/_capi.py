@@ -85,6 +85,9 @@ SIGNATURES = {
     "qsim_ipc_import": (C.c_int, [C.c_int, C.c_char_p, c_void_pp]),
     "qsim_ipc_release": (C.c_int, [C.c_void_p]),
     "qsim_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qsim_ipc_export_ex": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]),
+    "qsim_exchange_p2p": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "qsim_launch_count": (C.c_int64, []),
 }
 

@@ -161,6 +161,10 @@ int qsim_peer_free(void* ptr) { free(ptr); return QSIM_OK; }
 int qsim_ipc_export(void*, unsigned char*) { return qs::fail(QSIM_ERR_UNSUPPORTED, "no IPC in the host emulator"); }
 int qsim_ipc_import(int, const unsigned char*, void**) { return qs::fail(QSIM_ERR_UNSUPPORTED, "no IPC in the host emulator"); }
 int qsim_ipc_release(void*) { return QSIM_OK; }
+int qsim_ipc_export_ex(void*, unsigned char*, uint64_t*) { return qs::fail(QSIM_ERR_UNSUPPORTED, "no IPC in the host emulator"); }
+int qsim_exchange_p2p(void*, void* const*, int, int, const int*, const int*, const int*, void*) {
+  return qs::fail(QSIM_ERR_UNSUPPORTED, "no peer memory in the host emulator (the exchange goes through send/recv)");
+}
 int qsim_peer_copy(void* dst, const void* src, uint64_t bytes, void*) {
   if (!dst || !src) return qs::fail(QSIM_ERR_ARG, "qsim_peer_copy: null argument");
   memcpy(dst, src, bytes);

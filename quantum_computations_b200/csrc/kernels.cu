@@ -150,7 +150,7 @@ __device__ __forceinline__ void tma_box_coords(const QsPass& P, const QsTmaGeom&
 // The three CTAs of an SM are in different phases, so one CTA's fill and drain overlap
 // the steps of the other two.
 template <int MAXR, bool DENSE>
-__global__ void __launch_bounds__(QS_THREADS, (MAXR <= 3 ? 3 : 2))
+__global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1) : (MAXR <= 3 ? 3 : 2)))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_constant__ CUtensorMap tmap,
             const __grid_constant__ QsTmaGeom G, uint64_t ntiles) {
   extern __shared__ __align__(1024) unsigned char qs_smem[];
@@ -421,6 +421,53 @@ __global__ void k_swap_unpack(qs_c128* __restrict__ shard, const qs_c128* __rest
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < count;
        r += (uint64_t)gridDim.x * blockDim.x)
     shard[qs_deposit(first + r, sel)] = buf[r];
+}
+
+// One k-qubit exchange as ONE kernel over NVLink peer memory: gather, transfer and scatter
+// fused.  With k rank qubits trading places with k local qubits, rank R swaps, with each of the
+// 2^k - 1 partners R ^ d, the block of its shard whose k local bits spell the PARTNER's rank
+// bits against the partner's block whose local bits spell R's -- in place on both sides.
+// Every pair of amplitudes is handled by exactly one of the two ranks (alternating 512-byte
+// runs: the lower rank takes the even ones), which loads its own element and the partner's
+// (P2P load), and stores them crosswise (P2P store): each element crosses NVLink once, is
+// read from HBM once and written once, and no staging buffer exists.  The caller brackets the
+// launch with two stream-ordered barriers over the ranks (sharded.py).
+struct ExchGeom {
+  int k, n_local;
+  int pos[8];                 // local bit positions, ascending
+  int mine[8];                // this rank's value of the rank bit traded against pos[i]
+  qs_c128* peer[256];         // peer[d]: partner shard for the bit pattern d (over pos[] order); [0] unused
+  unsigned char higher[256];  // higher[d] = 1 if this rank's number is above the partner's
+};
+constexpr int kExchSplitBit = 5;
+
+__global__ void __launch_bounds__(256)
+k_exchange_p2p(qs_c128* __restrict__ shard, const __grid_constant__ ExchGeom G) {
+  const int k = G.k;
+  const uint64_t half = 1ull << (G.n_local - k - 1);          // amplitudes per partner that THIS rank moves
+  const uint64_t total = half * ((1ull << k) - 1ull);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += stride) {
+    const int d = 1 + (int)(w / half);
+    const uint64_t q = w % half;
+    // r: index inside the block; bit kExchSplitBit says which of the two ranks moves it
+    const uint64_t low = q & ((1ull << kExchSplitBit) - 1ull);
+    const uint64_t r = ((q >> kExchSplitBit) << (kExchSplitBit + 1)) | ((uint64_t)G.higher[d] << kExchSplitBit) | low;
+    uint64_t mine_idx = r, theirs_idx = r;
+#pragma unroll 1
+    for (int i = 0; i < k; ++i) {
+      const uint64_t lo_m = mine_idx & ((1ull << G.pos[i]) - 1ull);
+      const uint64_t lo_t = theirs_idx & ((1ull << G.pos[i]) - 1ull);
+      const uint64_t vd = (uint64_t)(G.mine[i] ^ ((d >> i) & 1));    // partner's rank bit
+      mine_idx = ((mine_idx >> G.pos[i]) << (G.pos[i] + 1)) | (vd << G.pos[i]) | lo_m;
+      theirs_idx = ((theirs_idx >> G.pos[i]) << (G.pos[i] + 1)) | ((uint64_t)G.mine[i] << G.pos[i]) | lo_t;
+    }
+    qs_c128* remote = G.peer[d] + theirs_idx;
+    const qs_c128 x = shard[mine_idx];
+    const qs_c128 y = *remote;
+    *remote = x;
+    shard[mine_idx] = y;
+  }
 }
 
 unsigned stream_grid(const DevCtx* ctx, uint64_t count, int threads) {
@@ -763,6 +810,74 @@ int qsim_ipc_import(int device, const unsigned char* handle64, void** out_ptr) {
 
 int qsim_ipc_release(void* imported_ptr) {
   if (imported_ptr) QS_CUDA(cudaIpcCloseMemHandle(imported_ptr));
+  return QSIM_OK;
+}
+
+int qsim_ipc_export_ex(void* ptr, unsigned char* handle64, uint64_t* offset) {
+  if (!ptr || !handle64 || !offset) return qs::fail(QSIM_ERR_ARG, "qsim_ipc_export_ex: null argument");
+  cudaIpcMemHandle_t h;
+  QS_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  // the handle names the whole allocation: find its base through the driver
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return (RangeFn)p;
+  }();
+  if (!range) return qs::fail(QSIM_ERR_CUDA, "cuMemGetAddressRange is not available");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
+    return qs::fail(QSIM_ERR_CUDA, "cuMemGetAddressRange failed");
+  *offset = (uint64_t)((CUdeviceptr)ptr - base);
+  return QSIM_OK;
+}
+
+int qsim_exchange_p2p(void* shard, void* const* peer_shards, int n_local, int nbits, const int* local_qubits,
+                      const int* my_bits, const int* partner_is_lower, void* stream) {
+  if (!shard || !peer_shards || !local_qubits || !my_bits || !partner_is_lower)
+    return qs::fail(QSIM_ERR_ARG, "qsim_exchange_p2p: null argument");
+  if (nbits < 1 || nbits > 8 || n_local - nbits - 1 < kExchSplitBit)
+    return qs::fail(QSIM_ERR_ARG, "qsim_exchange_p2p: bad sizes (blocks must hold at least 64 amplitudes)");
+  ExchGeom G;
+  memset(&G, 0, sizeof(G));
+  G.k = nbits;
+  G.n_local = n_local;
+  // order the bits by local position (ascending); pattern bit i of d stays with the caller's bit i
+  int order[8];
+  for (int i = 0; i < nbits; ++i) order[i] = i;
+  for (int i = 1; i < nbits; ++i)
+    for (int j = i; j > 0 && local_qubits[order[j]] > local_qubits[order[j - 1]]; --j) std::swap(order[j], order[j - 1]);
+  for (int i = 0; i < nbits; ++i) {
+    const int q = local_qubits[order[i]];
+    if (q < 0 || q >= n_local || (my_bits[order[i]] | 1) != 1) return qs::fail(QSIM_ERR_ARG, "qsim_exchange_p2p: bad qubit or bit");
+    G.pos[i] = n_local - 1 - q;                    // reference-style local qubit -> index bit
+    G.mine[i] = my_bits[order[i]];
+    if (i > 0 && G.pos[i] <= G.pos[i - 1]) return qs::fail(QSIM_ERR_ARG, "qsim_exchange_p2p: repeated qubit");
+  }
+  for (int d = 1; d < (1 << nbits); ++d) {
+    // the caller's pattern d (bit i <-> its bit i) in sorted order
+    int ds = 0;
+    for (int i = 0; i < nbits; ++i) ds |= ((d >> order[i]) & 1) << i;
+    if (!peer_shards[d]) return qs::fail(QSIM_ERR_ARG, "qsim_exchange_p2p: missing peer pointer");
+    G.peer[ds] = (qs_c128*)peer_shards[d];
+    G.higher[ds] = partner_is_lower[d] ? 1 : 0;
+  }
+  Bound bound;
+  int rc = bind_device(shard, &bound);
+  if (rc != QSIM_OK) return rc;
+  const uint64_t total = (1ull << (n_local - nbits - 1)) * ((1ull << nbits) - 1ull);
+  uint64_t blocks = (total + 255) / 256;
+  const uint64_t cap = (uint64_t)bound.ctx->sms * 8;
+  if (blocks > cap) blocks = cap;
+  k_exchange_p2p<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((qs_c128*)shard, G);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
   return QSIM_OK;
 }
 

@@ -83,21 +83,37 @@ enum QsFactorForm : uint8_t {
 #define QS_LF_PHASE  2u   // the layer has a phase table
 #define QS_LF_FINAL  4u   // sign block also carries the work-item-common part (final layer)
 
-struct QsLayer {
+// head word of a layer (everything the kernel branches on, one uniform load)
+#define QS_LH_SIGN     (1u << 0)
+#define QS_LH_PHASE    (1u << 1)
+#define QS_LH_FINAL    (1u << 2)
+#define QS_LH_GENERAL  (1u << 3)
+#define QS_LH_DENSE    (1u << 4)
+#define QS_LH_TAN(f)    (1u << (8 + (f)))
+#define QS_LH_SHEAR3(f) (1u << (12 + (f)))
+#define QS_LH_FULL(f)   (1u << (16 + (f)))
+
+struct alignas(16) QsLayer {
+  // ---- first 16 bytes: what the kernel reads per layer (one 128-bit uniform load) ----
+  uint32_t head;                 // QS_LH_* bits
+  uint16_t coef_off;             // ROT: 2 r doubles; GENERAL: 8 r doubles; DENSE: 2 * 4^r doubles (even)
+  uint16_t ph_off;               // 2^r complex (amplitude m: matrix factor f is bit r-1-f of m) (even)
+  uint32_t ngp[2];               // ng[0] | ng[1] << 16, ng[2] | ng[3] << 16
+  // ---- the rest is read by the planner, the emulator and the per-tile sign thread ----
   uint8_t  kind;
   uint8_t  flags;
   uint8_t  form[QS_MAX_R];       // per group factor (QsFactorForm)
   uint8_t  step;                 // the step this layer belongs to
   uint8_t  pad;
-  uint16_t coef_off;             // ROT: 2 r doubles; GENERAL: 8 r doubles; DENSE: 2 * 4^r doubles
-  uint16_t ph_off;               // 2^r complex (amplitude m: matrix factor f is bit r-1-f of m)
   uint16_t pair_off;             // first (local position, outer global bit) pair in QsPass::pairs
   uint16_t n_lo;
   uint16_t zconst;               // local positions carrying a Z
-  uint16_t pad1;                 // (sign pairs inside the group depend on m only: folded into the phase
-                                 //  table, or into the dense matrix, by the planner)
-  uint16_t ng[QS_MAX_R];         // in-tile partners (local positions outside the group) of group factor f
+  uint16_t pad1;
+  // in-tile partners (local positions outside the group) of group factor f live in ngp; sign
+  // pairs inside the group depend on m only and are folded into the phase table (or the
+  // dense matrix) by the planner
 };
+static_assert(sizeof(QsLayer) == 32, "QsLayer layout");
 
 struct QsStep {
   uint8_t  r;                    // number of group bits
@@ -128,9 +144,9 @@ struct QsPass {
   uint16_t fin_neigh[QS_MAX_WORK];   // XOR of fin_nsym over the bits of jhi_i
   uint16_t fin_nsym[QS_MAX_T];   // fin_nsym[p]: local positions (outside the last group) coupled to p
   QsStep   steps[QS_MAX_STEPS];
-  QsLayer  layers[QS_MAX_LAYERS];
+  alignas(16) QsLayer layers[QS_MAX_LAYERS];
   uint8_t  pairs[QS_MAX_PAIRS * 2];
-  double   coef[QS_MAX_COEF];
+  alignas(16) double coef[QS_MAX_COEF];
 };
 
 // CUDA kernel parameters are limited to 32764 bytes (CUDA >= 12.1, sm_70+); the pass shares

@@ -31,8 +31,8 @@ qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   if (opt) o = *opt;
   if (o.tile_bits <= 0) o.tile_bits = 12;
   if (o.low_bits <= 0) o.low_bits = 4;
-  if (o.max_group <= 0) o.max_group = 3;
-  if (o.max_dense_ops <= 0) o.max_dense_ops = 20;
+  if (o.max_group <= 0) o.max_group = 4;
+  if (o.max_dense_ops <= 0) o.max_dense_ops = 28;
   if (o.lookahead <= 0) o.lookahead = 600;
   if (o.merge_1q <= 0) o.merge_1q = 1;
   if (o.max_layers <= 0) o.max_layers = 4;
@@ -677,7 +677,8 @@ struct Walker {
           } else if (ga || gb) {
             const int pg = ga ? pa : pb, po = ga ? pb : pa, bo = ga ? b : a;
             if (po >= 0) {
-              L.ng[factor_of(pg)] ^= (uint16_t)(1u << po);
+              const int fg = factor_of(pg);
+              L.ngp[fg >> 1] ^= (1u << po) << (16 * (fg & 1));
             } else {
               P.pairs[2 * npairs] = (uint8_t)pg; P.pairs[2 * npairs + 1] = (uint8_t)bo; ++npairs; L.n_lo++;
             }
@@ -747,6 +748,21 @@ struct Walker {
         }
       }
       st.nlayers = (uint8_t)count;
+    }
+    for (int l = 0; l < nl; ++l) {               // the head words the kernel branches on
+      QsLayer& L = P.layers[l];
+      uint32_t h = 0;
+      if (L.flags & QS_LF_SIGN) h |= QS_LH_SIGN;
+      if (L.flags & QS_LF_PHASE) h |= QS_LH_PHASE;
+      if (L.flags & QS_LF_FINAL) h |= QS_LH_FINAL;
+      if (L.kind == QS_LAYER_GENERAL) h |= QS_LH_GENERAL;
+      if (L.kind == QS_LAYER_DENSE) h |= QS_LH_DENSE;
+      for (int f = 0; f < QS_MAX_R; ++f) {
+        if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_TAN) h |= QS_LH_TAN(f);
+        if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_SHEAR3) h |= QS_LH_SHEAR3(f);
+        if (L.kind == QS_LAYER_GENERAL && L.form[f] == QS_FORM_FULL) h |= QS_LH_FULL(f);
+      }
+      L.head = h;
     }
     P.nlayers = (uint32_t)nl;
     P.ncoef = (uint32_t)ncoef;

@@ -175,31 +175,59 @@ QS_HD void qs_rot_shear3(double p, double q, qs_c128& a0, qs_c128& a1) {
   a0.y = qs_fma(-p, a1.y, a0.y);
 }
 
-// Sign masks of the 2^R amplitudes of a work item for layer L: bit 31 of S[m] says whether
-// amplitude m is negated.  (The pairs inside the group depend on m only; the planner folds
-// them into the layer's phase table.)
+// The 16 bytes of a layer that the step loop needs, fetched as one 128-bit (uniform) load.
+struct QsLayerHot { uint32_t head, offs, ngp0, ngp1; };
+QS_HD QsLayerHot qs_layer_hot(const QsPass& P, int l) {
+#if defined(__CUDA_ARCH__)
+  const uint4 v = *reinterpret_cast<const uint4*>(&P.layers[l]);
+  QsLayerHot h; h.head = v.x; h.offs = v.y; h.ngp0 = v.z; h.ngp1 = v.w;
+  return h;
+#else
+  const QsLayer& L = P.layers[l];
+  QsLayerHot h; h.head = L.head; h.offs = (uint32_t)L.coef_off | ((uint32_t)L.ph_off << 16);
+  h.ngp0 = L.ngp[0]; h.ngp1 = L.ngp[1];
+  return h;
+#endif
+}
+struct alignas(16) qs_d2 { double x, y; };
+QS_HD qs_d2 qs_coef2(const QsPass& P, uint32_t off) {      // two doubles at an even offset: one 128-bit load
+  return *reinterpret_cast<const qs_d2*>(P.coef + off);
+}
+
+// Sign words of the 2^R amplitudes of a work item for a layer: BIT 31 of S[m] says whether
+// amplitude m is negated (the lower bits are garbage; qs_flip masks them).  (The pairs
+// inside the group depend on m only; the planner folds them into the layer's phase table.)
+//   W_f = z_f + parity(j0 & ng[f]);  amplitude m is negated iff parity(m & W) (+ the common bit)
 template <int R>
-QS_HD void qs_layer_sign(const QsPass& P, const QsLayer& L, uint32_t zl, uint32_t j0, uint32_t jlo, uint32_t i,
+QS_HD void qs_layer_sign(const QsPass& P, const QsLayerHot& H, uint32_t zl, uint32_t j0, uint32_t jlo, uint32_t i,
                          uint32_t fin_g, uint32_t fin_qlo, uint32_t* S) {
   constexpr int NA = 1 << R;
-  // W_f = z_f + parity(j0 & ng[f]); amplitude m is negated iff parity(m & W) (+ the common bit)
-  uint32_t M[R];                       // M[b]: all-ones iff bit b of W is set (bit b of m <-> factor R-1-b)
+  uint32_t V[R];                       // V[b] bit 31 = bit b of W (bit b of m <-> factor R-1-b)
 #pragma unroll
-  for (int f = 0; f < R; ++f)
-    M[R - 1 - f] = 0u - (((zl >> (R - 1 - f)) ^ qs_par(j0 & (uint32_t)L.ng[f])) & 1u);
+  for (int f = 0; f < R; ++f) {
+    const uint32_t ng = (f & 1) ? ((f >> 1 ? H.ngp1 : H.ngp0) >> 16) : (f >> 1 ? H.ngp1 : H.ngp0);
+    // j0 has no bits above position 15, so the packed partner of an even factor needs no mask;
+    // the Z bit of the factor (bit R-1-f of zl) goes into the same popcount
+    const uint32_t t = (j0 & ng) ^ (zl & (1u << (R - 1 - f)));
+#if defined(__CUDA_ARCH__)
+    V[R - 1 - f] = (uint32_t)__popc(t) << 31;
+#else
+    V[R - 1 - f] = (uint32_t)__builtin_popcount(t) << 31;
+#endif
+  }
   uint32_t C = 0u;
-  if (L.flags & QS_LF_FINAL) {
+  if (H.head & QS_LH_FINAL) {
     // pairs that touch no group bit: g + z.j0 + Q(jlo) + Q(jhi) + B(jlo, jhi)
     const uint32_t c0 = fin_g ^ qs_par(j0 & (zl >> 16)) ^ fin_qlo ^ (((uint32_t)P.fin_qhi >> i) & 1u) ^
                         qs_par(jlo & (uint32_t)P.fin_neigh[i]);
-    C = 0u - (c0 & 1u);
+    C = c0 << 31;
   }
 #pragma unroll
   for (int m = 0; m < NA; ++m) {
     uint32_t v = C;
 #pragma unroll
     for (int b = 0; b < R; ++b)
-      if ((m >> b) & 1) v ^= M[b];
+      if ((m >> b) & 1) v ^= V[b];
     S[m] = v;
   }
 }
@@ -209,7 +237,11 @@ QS_HD void qs_layer_sign(const QsPass& P, const QsLayer& L, uint32_t zl, uint32_
 // Amplitude m of a work item has local index j0 ^ dep[m]; group factor f is bit
 // (R-1-f) of m and sits at local position gpos[f].  zm[l] = qs_layer_z of layer l for
 // this tile; fin_g = qs_fin_g; fin_qlo = Q(jlo) of the final layer for this thread.
-template <int R, bool DENSE>
+// ZASM (device only): read zm through a plain 32-bit shared address (inline PTX).  It changes
+// nothing but the register allocation: measured on B200 the 16-amplitude instantiation needs it
+// to stay under 128 registers without spills (2 CTAs/SM), the 8-amplitude one is 10 % faster
+// without it.
+template <int R, bool DENSE, bool ZASM>
 QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
                          const uint32_t* zm, uint32_t fin_g, uint32_t fin_qlo, const QsStepTab& tab) {
   const QsStep& st = P.steps[s];
@@ -219,6 +251,9 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   const uint32_t jlo = qs_thread_jlo(tab, tid);
   const uint32_t slo = qs_swz(jlo);
   char* const t0 = reinterpret_cast<char*>(tile);
+#if defined(__CUDA_ARCH__)
+  const uint32_t zm_s = ZASM ? (uint32_t)__cvta_generic_to_shared(zm) : 0u;
+#endif
 
   // uniform trip count and no divergent exit, so that the compiler can keep the layer data on
   // the uniform datapath; a tile smaller than the CTA leaves the upper threads idle (they
@@ -238,23 +273,33 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
     bool stored = false;
 #pragma unroll 1
     for (int l = (int)st.layer0; l < l_end; ++l) {
-      const QsLayer& L = P.layers[l];
-      const uint32_t flags = L.flags;
-      if (flags & QS_LF_SIGN) {
+      const QsLayerHot H = qs_layer_hot(P, l);
+      const uint32_t head = H.head;
+      if (head & QS_LH_SIGN) {
+        uint32_t zl;
+#if defined(__CUDA_ARCH__)
+        if (ZASM) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zl) : "r"(zm_s + 4u * (uint32_t)l));
+        else zl = zm[l];
+#else
+        zl = zm[l];
+#endif
         uint32_t S[NA];
-        qs_layer_sign<R>(P, L, zm[l], j0, jlo, i, fin_g, fin_qlo, S);
+        qs_layer_sign<R>(P, H, zl, j0, jlo, i, fin_g, fin_qlo, S);
 #pragma unroll
         for (int m = 0; m < NA; ++m) qs_flip(a[m], S[m]);
       }
-      if (DENSE && L.kind == QS_LAYER_DENSE) {
+      if (DENSE && (head & QS_LH_DENSE)) {
         // dense 2^R x 2^R matrix: inputs are all in registers, so rows can be
         // written back one at a time (rolled loop keeps the code small)
-        const double* mat = P.coef + L.coef_off;
+        const double* mat = P.coef + (H.offs & 0xffffu);
         // the only layer that may follow a dense one is the pass's final sign layer
         uint32_t S2[NA];
 #pragma unroll
         for (int m = 0; m < NA; ++m) S2[m] = 0u;
-        if (l + 1 < l_end) qs_layer_sign<R>(P, P.layers[l + 1], zm[l + 1], j0, jlo, i, fin_g, fin_qlo, S2);
+        if (l + 1 < l_end) {
+          const QsLayerHot H2 = qs_layer_hot(P, l + 1);
+          qs_layer_sign<R>(P, H2, zm[l + 1], j0, jlo, i, fin_g, fin_qlo, S2);
+        }
         uint32_t sg2 = 0u;               // bit `row` set: negate that output (a rolled loop cannot index S2)
 #pragma unroll
         for (int m = 0; m < NA; ++m) sg2 |= (S2[m] >> 31) << m;
@@ -272,41 +317,43 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           if (active) *reinterpret_cast<qs_c128*>(t0 + (s0b ^ st.sdepb[row])) = o;
         }
         stored = true;
-        break;                               // a dense layer is the last layer of its step
+        break;                               // a dense layer is the last gate layer of its step
       }
-      if (flags & QS_LF_PHASE) {
-        const double* ph = P.coef + L.ph_off;
+      if (head & QS_LH_PHASE) {
+        const uint32_t ph_off = H.offs >> 16;
 #pragma unroll
         for (int m = 0; m < NA; ++m) {
           // two products into temporaries, then both components updated in place
-          const double pr = ph[2 * m], pi = ph[2 * m + 1];
-          const double t1 = pi * a[m].y, t2 = pi * a[m].x;
-          a[m].x = qs_fma(pr, a[m].x, -t1);
-          a[m].y = qs_fma(pr, a[m].y, t2);
+          const qs_d2 ph = qs_coef2(P, ph_off + 2 * m);
+          const double t1 = ph.y * a[m].y, t2 = ph.y * a[m].x;
+          a[m].x = qs_fma(ph.x, a[m].x, -t1);
+          a[m].y = qs_fma(ph.x, a[m].y, t2);
         }
       }
-      if (L.kind == QS_LAYER_ROT) {
+      if (!(head & QS_LH_GENERAL)) {
+        const uint32_t coef_off = H.offs & 0xffffu;
 #pragma unroll
         for (int f = 0; f < R; ++f) {
-          const uint32_t form = L.form[f];
-          const double c0 = P.coef[L.coef_off + 2 * f], c1 = P.coef[L.coef_off + 2 * f + 1];
           const int bit = 1 << (R - 1 - f);
-          if (form == QS_FORM_TAN) {
+          if (head & QS_LH_TAN(f)) {
+            const qs_d2 cf = qs_coef2(P, coef_off + 2 * f);
 #pragma unroll
             for (int m = 0; m < NA; ++m)
-              if (!(m & bit)) qs_rot_tan(c0, c1, a[m], a[m | bit]);
-          } else if (form == QS_FORM_SHEAR3) {
+              if (!(m & bit)) qs_rot_tan(cf.x, cf.y, a[m], a[m | bit]);
+          } else if (head & QS_LH_SHEAR3(f)) {
+            const qs_d2 cf = qs_coef2(P, coef_off + 2 * f);
 #pragma unroll
             for (int m = 0; m < NA; ++m)
-              if (!(m & bit)) qs_rot_shear3(c0, c1, a[m], a[m | bit]);
+              if (!(m & bit)) qs_rot_shear3(cf.x, cf.y, a[m], a[m | bit]);
           }
         }
       } else {
         // general complex 2x2 per factor (non-unitary user matrices): rare, keep it small
+        const uint32_t coef_off = H.offs & 0xffffu;
 #pragma unroll 1
         for (int f = 0; f < R; ++f) {
-          if (L.form[f] != QS_FORM_FULL) continue;
-          const double* mat = P.coef + L.coef_off + 8 * f;
+          if (!(head & QS_LH_FULL(f))) continue;
+          const double* mat = P.coef + coef_off + 8 * f;
           // pairs along factor f (f is a run-time value here): enumerate with a switch so
           // that the amplitude indices stay compile-time constants
           if (R >= 1 && f == 0) {
@@ -341,10 +388,11 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 template <int MAXR, bool DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
                              const uint32_t* zm, uint32_t fin_g, uint32_t fin_qlo, const QsStepTab& tab) {
+  constexpr bool ZASM = MAXR >= 4;
   const int r = P.steps[s].r;
-  if (r == 1) qs_phase_step<1, false>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
-  else if (r == 2) qs_phase_step<2, DENSE>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
-  else if (r == 3) qs_phase_step<3, DENSE>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  if (r == 1) qs_phase_step<1, false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (r == 2) qs_phase_step<2, DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (r == 3) qs_phase_step<3, DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
   else if (MAXR >= 4 && r == 4)
-    qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
 }

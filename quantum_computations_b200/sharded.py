@@ -102,7 +102,10 @@ class ShardedState:
         self.buf = self.backend.empty(1 << self.n_local)
         self.swaps = 0
         self.swap_seconds = 0.0
+        self.amps_sent = 0
         self._peer = None
+        self._p2p = None                          # peers' shards mapped through CUDA IPC (fused exchange)
+        self._swap_events = []                    # CUDA event pairs of the fused exchanges (timed lazily)
         # how to view a backend buffer as a torch tensor for the communicator
         self._as_torch = as_torch or (lambda b: b)
 
@@ -169,6 +172,11 @@ class ShardedState:
         be, lib = self.backend, self.backend.lib
         if self._peer is not None and self._peer["chunk"] == chunk:
             return self._peer
+        if self._peer is not None:                # another chunk size: give the old staging back first
+            p2p = self._p2p
+            self._p2p = None
+            self.close()
+            self._p2p = p2p
         use_ipc = getattr(be, "name", "") == "cuda" and os.environ.get("QSIM_SWAP_IPC", "1") != "0"
         peer = {"chunk": chunk, "ipc": use_ipc}
         if not use_ipc:
@@ -205,6 +213,110 @@ class ShardedState:
         peer["token_in"] = torch.zeros(2, dtype=torch.float64, device=be.device)
         self._peer = peer
         return peer
+
+    # -- fused exchange over NVLink peer memory (GPUs) ---------------------------------------------
+    def _use_fused(self, block: int) -> bool:
+        return (getattr(self.backend, "name", "") == "cuda" and os.environ.get("QSIM_SWAP_FUSED", "1") != "0"
+                and os.environ.get("QSIM_SWAP_IPC", "1") != "0" and block >= 64)
+
+    def _p2p_setup(self):
+        """Map every other rank's shard into this process (CUDA IPC), once per shard buffer."""
+        be, lib = self.backend, self.backend.lib
+        key = (be.ptr(self.buf), self.n_local)
+        if self._p2p is not None and self._p2p["key"] == key:
+            return self._p2p
+        self._p2p_release()
+        import torch
+        h = C.create_string_buffer(64)
+        off = C.c_uint64(0)
+        _capi.check(lib, lib.qsim_ipc_export_ex(C.c_void_p(key[0]), h, C.byref(off)))
+        gathered = self.comm.allgather_object((h.raw, int(off.value), key[1]))
+        if any(item[2] != self.n_local for item in gathered):
+            raise RuntimeError("the ranks disagree on the shard size")
+        shards, opened = {}, []
+        for r, (handle, offset, _nl) in enumerate(gathered):
+            if r == self.comm.rank:
+                continue
+            out = C.c_void_p()
+            _capi.check(lib, lib.qsim_ipc_import(be.device.index, handle, C.byref(out)))
+            opened.append(out.value)
+            shards[r] = out.value + offset
+        self._p2p = {"key": key, "shards": shards, "opened": opened,
+                     "token": torch.zeros(1, dtype=torch.float32, device=be.device)}
+        return self._p2p
+
+    def _p2p_release(self):
+        p2p, self._p2p = self._p2p, None
+        if p2p is None:
+            return
+        self.backend.synchronize()
+        for ptr in p2p["opened"]:
+            self.backend.lib.qsim_ipc_release(C.c_void_p(ptr))
+
+    def _rank_barrier(self, token) -> None:
+        """Stream-ordered barrier over the ranks: a one-element all-reduce on the compute stream."""
+        self.comm.dist.all_reduce(token, group=self.comm.group)
+
+    def _exchange_fused(self, pairs, gis, qubits, mine, block: int) -> None:
+        """The whole exchange as one kernel per rank (``qsim_exchange_p2p``): gather, NVLink
+        transfer and scatter fused, in place in both shards, bracketed by two stream-ordered
+        barriers.  Nothing here synchronises the host."""
+        import torch
+        be, lib = self.backend, self.backend.lib
+        k = len(pairs)
+        p2p = self._p2p_setup()
+        peers = (C.c_void_p * (1 << k))()
+        lower = (C.c_int * (1 << k))()
+        for d in range(1, 1 << k):
+            partner = self.comm.rank
+            for i in range(k):
+                partner ^= ((d >> i) & 1) << gis[i]
+            peers[d] = p2p["shards"][partner]
+            lower[d] = 1 if partner < self.comm.rank else 0
+        my_bits = (C.c_int * k)(*mine)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self._rank_barrier(p2p["token"])           # every rank has finished the passes before the exchange
+        _capi.check(lib, lib.qsim_exchange_p2p(be.ptr(self.buf), peers, self.n_local, k, qubits, my_bits, lower,
+                                               be.stream()))
+        self._rank_barrier(p2p["token"])           # every rank's kernel is done: the shards are whole again
+        ev1.record()
+        self._swap_events.append((ev0, ev1))
+        self.swaps += 1
+        self.amps_sent += ((1 << k) - 1) * block
+        self.comm.bytes_exchanged += 16 * ((1 << k) - 1) * block
+        for gp, lp in pairs:
+            la, lb = self.phys.index(gp), self.phys.index(lp)
+            self.phys[la], self.phys[lb] = lp, gp
+
+    def collect_swap_time(self) -> float:
+        """Fold the device time of the fused exchanges issued so far into ``swap_seconds``
+        (synchronises)."""
+        if self._swap_events:
+            self.backend.synchronize()
+            for ev0, ev1 in self._swap_events:
+                self.swap_seconds += 1e-3 * ev0.elapsed_time(ev1)
+            self._swap_events = []
+        return self.swap_seconds
+
+    def close(self) -> None:
+        """Release the peer mappings and the staging buffers of the exchanges."""
+        self._p2p_release()
+        peer, self._peer = self._peer, None
+        if peer is not None and peer.get("ipc"):
+            lib = self.backend.lib
+            self.backend.synchronize()
+            for opened in peer.get("remote_recv", {}).values():
+                for ptr in opened:
+                    lib.qsim_ipc_release(C.c_void_p(ptr))
+            for ptr in peer.get("send_ptr", []) + peer.get("recv_ptr", []):
+                lib.qsim_peer_free(C.c_void_p(ptr))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def swap(self, global_phys: int, local_phys: int) -> None:
         """Exchange one rank bit with one local bit (half a shard travels)."""
@@ -249,6 +361,9 @@ class ShardedState:
                 vals.append(mine[i] ^ di)
             for c in range(per_block):
                 items.append((partner, (C.c_int * k)(*vals), c * chunk))
+        if self._use_fused(block):
+            self._exchange_fused(pairs, gis, qubits, mine, block)
+            return
         peer = self._peer_setup(chunk)
         ipc = peer["ipc"]
         be.synchronize()                           # so the timer below sees the exchange alone
@@ -308,7 +423,7 @@ class ShardedState:
         be.synchronize()
         self.swap_seconds += time.perf_counter() - t0
         self.swaps += 1
-        self.amps_sent = getattr(self, "amps_sent", 0) + len(items) * chunk
+        self.amps_sent += len(items) * chunk
         # the logical bits trade places (flip flags stay with the rank bits)
         for gp, lp in pairs:
             la, lb = self.phys.index(gp), self.phys.index(lp)
@@ -353,10 +468,20 @@ class ShardedState:
                                                 part.ctypes.data_as(_capi.c_double_p), be.stream()))
         probs = self.comm.allreduce_sum(part)
         norm0, norm1 = np.sqrt(probs[0]), np.sqrt(probs[1])
-        pick = np.zeros(1)
+        # rank 0 draws (same generator, same stream consumption and same ValueError as the
+        # reference, DV/gates.py:183); a failure there is shared so that every rank raises
+        # instead of the others waiting in the next collective
+        pick = np.zeros(2)
+        error = None
         if self.comm.rank == 0:
-            pick[0] = forced if forced is not None else int(np.random.choice([0, 1], p=[norm0 ** 2, norm1 ** 2]))
-        outcome = int(round(self.comm.allreduce_sum(pick)[0]))
+            try:
+                pick[0] = forced if forced is not None else int(np.random.choice([0, 1], p=[norm0 ** 2, norm1 ** 2]))
+            except ValueError as exc:
+                pick[1], error = 1.0, exc
+        pick = self.comm.allreduce_sum(pick)
+        if pick[1] > 0:
+            raise error if error is not None else ValueError("probabilities do not sum to 1")
+        outcome = int(round(pick[0]))
         out = be.empty(1 << (self.n_local - 1))
         bra = vecs[outcome]
         _capi.check(lib, lib.qsim_collapse(be.ptr(self.buf), be.ptr(out), self.n_local, int(j),

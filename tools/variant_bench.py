@@ -18,6 +18,9 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from quantum_computations_b200 import _capi, engine, workloads  # noqa: E402
+
+if os.environ.get("QSIM_EXPERIMENT_LIB"):        # development builds of the library (other CTA sizes ...)
+    engine._LIB_PATH = os.path.abspath(os.environ["QSIM_EXPERIMENT_LIB"])
 from quantum_computations_b200.states import State  # noqa: E402
 
 
