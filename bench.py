@@ -45,6 +45,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "gates/sec (30q c128 random circuit, depth 200)"
 METRIC_SHARDED = "gates/sec (34q c128 random circuit, depth 200, sharded over the GPUs)"
+
+
+def metric_sharded(n: int, depth: int) -> str:
+    return f"gates/sec ({n}q c128 random circuit, depth {depth}, sharded over the GPUs)"
 ALT_MAX_DENSE = 8            # matrices per pass of the HBM-roof operating point (roofline_hbm_point)
 PASS_PARAM_BYTES = 28672     # sizeof(QsPass) + tensor map + geometry: kernel parameters per tile-pass launch
 # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
@@ -72,7 +76,7 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="skip the C1-C3 secondary entries")
     ap.add_argument("--rb-sequences", type=int, default=10000)
     ap.add_argument("--no-check", action="store_true", help="sharded: skip the circuit-then-inverse check")
-    ap.add_argument("--check-depth", type=int, default=8)
+    ap.add_argument("--check-depth", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -22,7 +22,7 @@ import numpy as np
 def run_sharded(args, world, rank, local_rank):
     import torch
     import torch.distributed as dist
-    from bench import (METRIC_SHARDED, PASS_PARAM_BYTES, ClockSampler, measured_peaks, plan_options, secondary_rb)
+    from bench import (PASS_PARAM_BYTES, ClockSampler, measured_peaks, metric_sharded, plan_options, secondary_rb)
     from quantum_computations_b200 import engine, sharded, workloads
     from quantum_computations_b200.states import State
 
@@ -120,7 +120,7 @@ def run_sharded(args, world, rank, local_rank):
         nvlink = sent_bytes / (swap_ms * 1e-3) / 1e9 if swaps else None
         raw = args.steps * ngates / (total_ms * 1e-3)
         line = {
-            "metric": METRIC_SHARDED, "value": raw, "unit": "gates/s", "n_gpus": world,
+            "metric": metric_sharded(n, args.depth), "value": raw, "unit": "gates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": {"workload": f"C5: {n}-qubit complex128 random circuit, depth {args.depth}, {ngates} gates, "

@@ -187,6 +187,27 @@ def gen_circuits(fast):
     save("circuits.npz", meta, arrays)
 
 
+def gen_circuits_rand():
+    """The C4 generator from RANDOM initial kets (N = 10, 11): every amplitude of the result is
+    distinct, unlike the few-valued vectors a shallow circuit leaves on |0...0>."""
+    rng = np.random.default_rng(2718)
+    meta, arrays = [], {}
+    for n, depth, seed in ((10, 3, 31), (11, 2, 32)):
+        t0 = time.time()
+        psi = rand_ket(n, rng)
+        circ = workloads.sv_random_circuit(n, depth, seed, gates=rg)
+        out = rsim.Simulator(circ).run(psi)
+        key = f"svr_n{n}_d{depth}_s{seed}"
+        arrays[key + "_in"] = psi
+        arrays[key] = out
+        meta.append({"kind": "sv_random_ket", "n": n, "depth": depth, "seed": seed, "in": key + "_in", "out": key,
+                     "ngates": len(circ), "distinct_amplitudes": int(len(np.unique(np.round(out, 12)))),
+                     "ref_seconds": time.time() - t0})
+        print(f"  reference ran {key}: {len(circ)} gates in {time.time() - t0:.1f} s, "
+              f"{meta[-1]['distinct_amplitudes']} distinct amplitudes")
+    save("circuits_rand.npz", meta, arrays)
+
+
 def gen_grover():
     import dv_circuits as ccs      # PAPER/dv_circuits.py
     import grover as pgrover       # PAPER/grover.py
@@ -400,6 +421,9 @@ if __name__ == "__main__":
     if "--only-tomography" in sys.argv:
         gen_tomography()
         sys.exit(0)
+    if "--only-circuits-rand" in sys.argv:
+        gen_circuits_rand()
+        sys.exit(0)
     gen_single_gates()
     gen_density_gates()
     gen_measure()
@@ -411,5 +435,6 @@ if __name__ == "__main__":
     gen_metrics()
     gen_sim_measure()
     gen_circuits(fast)
+    gen_circuits_rand()
     gen_layering()
     gen_tomography()

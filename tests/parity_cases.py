@@ -31,6 +31,10 @@ def load(name):
 
 
 def rel_err(got, ref) -> float:
+    """max |got - ref| / max |ref|: the error relative to the LARGEST reference entry (a norm-wise
+    bound, not element-wise relative error -- an amplitude that is 1e-6 of the largest one is
+    only checked to RTOL * 1e6 of its own size).  This is the sense in which the north star's
+    "<= 1e-10 relative" is asserted throughout, with RTOL = 1e-12."""
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape, (got.shape, ref.shape)
     scale = max(float(np.abs(ref).max()), 1e-300)
@@ -140,6 +144,15 @@ def check_sv_circuits(backend, plan_options=None, max_n=13):
         circ = workloads.sv_random_circuit(rec["n"], rec["depth"], rec["seed"])
         assert len(circ) == rec["ngates"]
         got = Simulator(circ, backend=backend, plan_options=plan_options).run([State.ZERO] * rec["n"])
+        worst = max(worst, rel_err(got, z[rec["out"]]))
+    # the same generator from random kets: every amplitude of these vectors is distinct
+    meta, z = load("circuits_rand.npz")
+    for rec in meta:
+        if rec["n"] > max_n:
+            continue
+        circ = workloads.sv_random_circuit(rec["n"], rec["depth"], rec["seed"])
+        assert len(circ) == rec["ngates"]
+        got = Simulator(circ, backend=backend, plan_options=plan_options).run(z[rec["in"]])
         worst = max(worst, rel_err(got, z[rec["out"]]))
     assert worst < RTOL, worst
     return worst
@@ -287,7 +300,7 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
 
 def check_edge_cases(backend):
     """The corners: empty and diagonal-only circuits, registers of one qubit, gates on the
-    whole register, gates wider than a step (out-of-place generic kernel, k = 5 .. 7),
+    whole register, gates wider than a step (in-place dense-block kernel, k = 5 .. 8),
     cancelling CZ pairs, reversed / scattered targets, empty and zero-length RB batches."""
     rng = np.random.default_rng(99)
 
@@ -336,13 +349,26 @@ def check_edge_cases(backend):
     got, ref = run_both(circ, psi, tile_bits=6, low_bits=1)
     assert rel_err(got, ref) < RTOL
 
-    # wider than a step: the out-of-place generic kernel, between fused segments
+    # wider than a step: the in-place dense-block kernel (DMMA), between fused segments
     for k, n in ((5, 7), (6, 8), (7, 7)):
         psi = rand_state(n)
         idx = [int(q) for q in rng.permutation(n)[:k]]
         circ = [gates.H(0), gates.CZ(0, n - 1), gates.Gate(idx, rand_unitary(k)), gates.T(idx[0]), gates.H(n - 1)]
         got, ref = run_both(circ, psi)
         assert rel_err(got, ref) < RTOL, (k, n)
+    # ... on registers with many tiles; targets on the lowest index bits (qubits n-1, n-2, n-3), on the
+    # highest, scattered; the same plan executed twice (the device copy of the matrix is reused)
+    for k, n, idx in ((5, 12, [11, 10, 9, 0, 4]), (5, 13, [0, 1, 2, 3, 4]), (6, 12, None), (7, 12, None),
+                      (8, 11, None), (5, 5, None), (6, 7, [6, 5, 4, 3, 2, 1])):
+        psi = rand_state(n)
+        if idx is None:
+            idx = [int(q) for q in rng.permutation(n)[:k]]
+        u = rand_unitary(k)
+        circ = [gates.Gate(idx, u), gates.CZ(0, n - 1), gates.Gate(idx, u.conj().T @ u @ u)]
+        sim = Simulator(circ, backend=backend)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        for _ in range(2):
+            assert rel_err(sim.run(psi), ref) < RTOL, (k, n, idx)
 
     # density matrix with a channel on a one-qubit register
     rho = np.array([[0.75, 0.1 - 0.2j], [0.1 + 0.2j, 0.25]])

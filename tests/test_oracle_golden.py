@@ -82,6 +82,20 @@ def test_circuits_strided():
         assert rel_err(got, z[rec["out"]]) < TOL
 
 
+def test_circuits_from_random_kets():
+    """C4 generator from random initial kets (every output amplitude distinct), N = 10 and 11:
+    both oracle modules against the reference's own output."""
+    meta, z = load("circuits_rand.npz")
+    for rec in meta:
+        assert rec["distinct_amplitudes"] == 2 ** rec["n"]
+        circ = workloads.sv_random_circuit(rec["n"], rec["depth"], rec["seed"])
+        got, _ = strided.run(as_oracle_ops(circ), z[rec["in"]])
+        assert rel_err(got, z[rec["out"]]) < TOL
+        if rec["n"] <= 10:
+            got, _ = dense_ref.run(as_oracle_ops(circ), z[rec["in"]])
+            assert rel_err(got, z[rec["out"]]) < TOL
+
+
 def test_circuits_dense_small():
     meta, z = load("circuits.npz")
     for rec in meta:
