@@ -49,7 +49,8 @@ METRIC_SHARDED = "gates/sec (34q c128 random circuit, depth 200, sharded over th
 
 def metric_sharded(n: int, depth: int) -> str:
     return f"gates/sec ({n}q c128 random circuit, depth {depth}, sharded over the GPUs)"
-ALT_MAX_DENSE = 8            # matrices per pass of the HBM-roof operating point (roofline_hbm_point)
+ALT_MAX_DENSE = 6            # matrices per pass of the HBM-roof operating point (roofline_hbm_point) ...
+ALT_MAX_GROUP = 3            # ... with 8 amplitudes per thread (3 CTAs per SM)
 PASS_PARAM_BYTES = 28672     # sizeof(QsPass) + tensor map + geometry: kernel parameters per tile-pass launch
 # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
 # `ncu --set full` capture summarised in profiles/r1_ncu_full_k_tile_pass_n30.csv (17.18 GB + 17.12 GB)
@@ -459,7 +460,7 @@ def run_b200(args):
     # the same circuit planned for the HBM roof instead of for gates/s: fewer gates per pass
     roofline_hbm_point = None
     if not args.no_alt and not any(opts.values()):
-        alt_opts = dict(opts, max_dense_ops=ALT_MAX_DENSE)
+        alt_opts = dict(opts, max_dense_ops=ALT_MAX_DENSE, max_group=ALT_MAX_GROUP)
         alt = engine.Plan(backend, n, ops, alt_opts)
         reset()
         alt.execute(state.buf)
@@ -482,26 +483,50 @@ def run_b200(args):
         import psutil
         need = 16 << n
         if psutil.virtual_memory().available > need * 1.5:
-            out = backend.pinned_empty(1 << n)
+            outs = [backend.pinned_empty(1 << n), backend.pinned_empty(1 << n)] \
+                if psutil.virtual_memory().available > need * 2.6 else [backend.pinned_empty(1 << n)]
             init = [State.ZERO] * n
             del state
             torch.cuda.empty_cache()
             sim = Simulator(circuit, plan_options=opts)
-            sim.run(init, out=out)                              # warm-up
+            sim.run(init, out=outs[0])                          # warm-up
+            # one call after the other, each blocking until its result is in host memory
             e2e_steps = max(1, min(args.steps, 2))
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                sim.run(init, out=out)
+                sim.run(init, out=outs[0])
             torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / e2e_steps
+            dt_serial = (time.perf_counter() - t0) / e2e_steps
+            # the same calls with block=False: step k+1 computes while the result of step k crosses
+            # PCIe (two device states, two pinned buffers); every result is waited for inside the
+            # timed region
+            dt = dt_serial
+            piped_steps = 0
+            if len(outs) == 2:
+                piped_steps = max(3, args.steps)
+                t0 = time.perf_counter()
+                pending = None
+                for k in range(piped_steps):
+                    nxt = sim.run(init, out=outs[k % 2], block=False)
+                    if pending is not None:
+                        pending.result()
+                    pending = nxt
+                pending.result()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / piped_steps
+            out = outs[0]
             assert abs(np.vdot(out[:1 << 20], out[:1 << 20]).real) >= 0.0
             h2d = passes * PASS_PARAM_BYTES + 64 * n            # kernel-parameter blocks + product-state amplitudes
             e2e = {"value": ngates / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": need,
-                   "seconds_per_step": dt, "steps": e2e_steps,
-                   "note": "Simulator(circuit).run([ZERO]*n, out=pinned): lowering, plan lookup (the plan compiled "
-                           "by the warm-up run is reused through the simulator's content-keyed cache; compiling takes "
-                           "config.plan_seconds), product state, all passes, 2^n x 16 B device-to-host copy"}
-            del out, sim
+                   "seconds_per_step": dt, "steps": piped_steps or e2e_steps,
+                   "blocking_calls": {"value": ngates / dt_serial, "seconds_per_step": dt_serial, "steps": e2e_steps},
+                   "note": "Simulator(circuit).run([ZERO]*n, out=pinned, block=False), result() of step k taken "
+                           "after step k+1 is queued: lowering, plan lookup (the plan compiled by the warm-up run is "
+                           "reused through the simulator's content-keyed cache; compiling takes config.plan_seconds), "
+                           "product state, all passes, 2^n x 16 B device-to-host copy of EVERY step inside the timed "
+                           "region, the copy of step k overlapping the passes of step k+1; blocking_calls is the "
+                           "same loop with block=True (no overlap)"}
+            del out, outs, sim
         else:
             e2e = {"value": None, "unit": "gates/s", "skipped": "host memory too small for the 2^n output buffer"}
     torch.cuda.empty_cache()

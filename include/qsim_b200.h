@@ -147,6 +147,20 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
                   const double* rho0, const double* psi0, double* out_fidelity, double* out_purity,
                   double* out_rho, void* stream);
 
+/* ---- Pauli-trajectory batch (mechanism of GKP/simulator.py:26-55 at the DV level) ---------
+ * `shots` noisy realisations of ONE circuit of 1- and 2-qubit gates on a ket of n_qubits <= 12:
+ * after gate g, on each of its qubits, an X and then a Z is applied where the shot's flip bits
+ * say so (flips[shot][...], two bytes per gate qubit in gate order: X, Z).  One CTA per shot,
+ * state in shared memory; the flips are folded into the gate's rows.  ops = n_ops x {k, bit0,
+ * bit1, matrix offset (in complex numbers) into `matrices`} as int32, bits are INDEX bits
+ * (reference qubit q is bit n-1-q), bit0 belongs to the first tensor factor.  psi0 /
+ * observable: 2^n complex.  out_fidelity[shot] = |<observable|psi>|^2 (optional),
+ * out_prob_sum[i] += sum over shots of |psi_i|^2 (optional, caller zeroes it), out_states:
+ * shots x 2^n complex (optional, for tests).  All pointers are DEVICE pointers. */
+int qsim_traj_batch(int n_qubits, int64_t shots, int n_ops, const int32_t* ops, const double* matrices,
+                    const uint8_t* flips, int64_t flips_per_shot, const double* psi0, const double* observable,
+                    double* out_fidelity, double* out_prob_sum, double* out_states, void* stream);
+
 /* ---- global<->local qubit exchange helpers for sharded states ----------------------
  * A state of n qubits sharded over 2^g ranks keeps g qubits in the rank number.
  * Exchanging k rank qubits with k local qubits at once is an all-to-all among the 2^k

@@ -134,3 +134,69 @@ QS_HD void qs_rb_sequence(const uint16_t* codes, int64_t len, const double* supe
   if (out_rho)
     for (int e = 0; e < D2; ++e) { out_rho[2 * e] = rho[e].x; out_rho[2 * e + 1] = rho[e].y; }
 }
+
+
+// ---- Pauli-trajectory batch (trajectories.py; mechanism of GKP/simulator.py:26-55 at the DV
+//      level): one shot = the circuit on a small ket with, after every gate and on each of its
+//      qubits, an X flip and then a Z flip where the shot's flip bits say so -------------------
+// A gate of the shared circuit: k = 1 or 2 qubits on index bits b0 (matrix factor 0, the
+// most significant bit of the row index) and b1; `mat` = offset of its row-major complex
+// matrix in the matrix table (in complex numbers).
+struct QsTrajOp { int32_t k, b0, b1, mat; };
+
+// Row r of (Z^z X^x M): X on a qubit swaps the rows that differ in its bit, Z negates the
+// rows where its bit is 1.  flips = {x0, z0[, x1, z1]} for the gate's qubits in order.
+QS_HD void qs_traj_rows(const QsTrajOp& op, const double* mats, const uint8_t* flips, qs_c128* M) {
+  const int dim = 1 << op.k;
+  int xmask = 0, zmask = 0;
+  for (int f = 0; f < op.k; ++f) {
+    xmask |= (flips[2 * f] ? 1 : 0) << (op.k - 1 - f);
+    zmask |= (flips[2 * f + 1] ? 1 : 0) << (op.k - 1 - f);
+  }
+  const double* src = mats + 2 * (size_t)op.mat;
+  for (int r = 0; r < dim; ++r) {
+    const double sgn = (qs_par((uint32_t)(r & zmask)) ? -1.0 : 1.0);
+    for (int c = 0; c < dim; ++c) {
+      M[r * dim + c].x = sgn * src[2 * ((r ^ xmask) * dim + c)];
+      M[r * dim + c].y = sgn * src[2 * ((r ^ xmask) * dim + c) + 1];
+    }
+  }
+}
+
+// Work items tid, tid + nthreads, ... of one gate on the 2^n amplitudes in `state`.
+QS_HD void qs_traj_apply(qs_c128* state, int n, const QsTrajOp& op, const qs_c128* M, uint32_t tid, uint32_t nthreads) {
+  if (op.k == 1) {
+    const uint64_t bit = 1ull << op.b0;
+    for (uint64_t w = tid; w < (1ull << (n - 1)); w += nthreads) {
+      const uint64_t i0 = qs_insert_bit(w, op.b0, 0);
+      const qs_c128 a0 = state[i0], a1 = state[i0 | bit];
+      qs_c128 o0, o1;
+      o0.x = M[0].x * a0.x - M[0].y * a0.y + M[1].x * a1.x - M[1].y * a1.y;
+      o0.y = M[0].x * a0.y + M[0].y * a0.x + M[1].x * a1.y + M[1].y * a1.x;
+      o1.x = M[2].x * a0.x - M[2].y * a0.y + M[3].x * a1.x - M[3].y * a1.y;
+      o1.y = M[2].x * a0.y + M[2].y * a0.x + M[3].x * a1.y + M[3].y * a1.x;
+      state[i0] = o0;
+      state[i0 | bit] = o1;
+    }
+  } else {
+    const int lo = op.b0 < op.b1 ? op.b0 : op.b1, hi = op.b0 < op.b1 ? op.b1 : op.b0;
+    for (uint64_t w = tid; w < (1ull << (n - 2)); w += nthreads) {
+      const uint64_t base = qs_insert_bit(qs_insert_bit(w, lo, 0), hi, 0);
+      uint64_t idx[4];
+      qs_c128 a[4];
+      for (int r = 0; r < 4; ++r) {
+        idx[r] = base | ((uint64_t)((r >> 1) & 1) << op.b0) | ((uint64_t)(r & 1) << op.b1);
+        a[r] = state[idx[r]];
+      }
+      for (int r = 0; r < 4; ++r) {
+        double re = 0.0, im = 0.0;
+        for (int c = 0; c < 4; ++c) {
+          re += M[4 * r + c].x * a[c].x - M[4 * r + c].y * a[c].y;
+          im += M[4 * r + c].x * a[c].y + M[4 * r + c].y * a[c].x;
+        }
+        state[idx[r]].x = re;
+        state[idx[r]].y = im;
+      }
+    }
+  }
+}

@@ -353,6 +353,41 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
   return QSIM_OK;
 }
 
+int qsim_traj_batch(int n_qubits, int64_t shots, int n_ops, const int32_t* ops, const double* matrices,
+                    const uint8_t* flips, int64_t flips_per_shot, const double* psi0, const double* observable,
+                    double* out_fidelity, double* out_prob_sum, double* out_states, void*) {
+  if (!ops || !matrices || !flips || !psi0) return qs::fail(QSIM_ERR_ARG, "qsim_traj_batch: null argument");
+  if (n_qubits < 1 || n_qubits > 12) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_traj_batch: 1 <= n_qubits <= 12");
+  if (shots < 0 || n_ops < 0 || flips_per_shot < 0) return qs::fail(QSIM_ERR_ARG, "qsim_traj_batch: bad sizes");
+  const uint64_t dim = 1ull << n_qubits;
+  const QsTrajOp* op = (const QsTrajOp*)ops;
+  std::vector<qs_c128> state(dim);
+  for (int64_t shot = 0; shot < shots; ++shot) {
+    memcpy(state.data(), psi0, sizeof(qs_c128) * dim);
+    const uint8_t* fl = flips + shot * flips_per_shot;
+    for (int o = 0; o < n_ops; ++o) {
+      qs_c128 M[16];
+      qs_traj_rows(op[o], matrices, fl, M);
+      fl += 2 * op[o].k;
+      qs_traj_apply(state.data(), n_qubits, op[o], M, 0, 1);
+    }
+    if (out_states) memcpy(out_states + 2 * (uint64_t)shot * dim, state.data(), sizeof(qs_c128) * dim);
+    double fr = 0.0, fi = 0.0;
+    for (uint64_t i = 0; i < dim; ++i) {
+      const qs_c128 v = state[i];
+      if (out_prob_sum) out_prob_sum[i] += v.x * v.x + v.y * v.y;
+      if (observable) {
+        const double wx = observable[2 * i], wy = observable[2 * i + 1];
+        fr += wx * v.x + wy * v.y;
+        fi += wx * v.y - wy * v.x;
+      }
+    }
+    if (observable && out_fidelity) out_fidelity[shot] = fr * fr + fi * fi;
+  }
+  ++g_launches;
+  return QSIM_OK;
+}
+
 static int swap_select(const char* who, int n_local, int nbits, const int* local_qubits, const int* bit_values,
                        uint64_t first, uint64_t count, QsBitSel* sel) {
   if (n_local < 1 || nbits < 1 || nbits > 8 || nbits > n_local || !local_qubits || !bit_values)

@@ -612,6 +612,69 @@ __global__ void __launch_bounds__(128) k_rb_batch(int64_t n_seq, const uint16_t*
 }
 
 // =====================================================================================
+// Pauli-trajectory batch: one CTA per shot, the ket (n <= 12 qubits) lives in shared memory
+// =====================================================================================
+// Every shot runs the same gate list; its random X / Z flips (bits prepared by the host from
+// the caller's generator) are folded into the rows of each gate's matrix, so a noisy shot
+// costs exactly what the noiseless circuit costs.  Outputs: |<obs|psi>|^2 per shot and the
+// sum over shots of |amplitude|^2 (each CTA accumulates its shots in registers and adds once).
+__global__ void __launch_bounds__(256)
+k_traj_batch(int n, int64_t shots, int nops, const QsTrajOp* __restrict__ ops, const double* __restrict__ mats,
+             const uint8_t* __restrict__ flips, int64_t flips_per_shot, const qs_c128* __restrict__ psi0,
+             const qs_c128* __restrict__ obs, double* out_fid, double* out_prob, qs_c128* out_states) {
+  extern __shared__ __align__(16) unsigned char qs_traj_smem[];
+  qs_c128* state = reinterpret_cast<qs_c128*>(qs_traj_smem);
+  __shared__ qs_c128 M[16];
+  __shared__ double red[2 * 8];
+  const uint32_t tid = threadIdx.x;
+  const uint64_t dim = 1ull << n;
+  double acc[16];                                   // n <= 12: at most 16 amplitudes per thread
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  for (int64_t shot = blockIdx.x; shot < shots; shot += gridDim.x) {
+    for (uint64_t i = tid; i < dim; i += 256) state[i] = psi0[i];
+    const uint8_t* fl = flips + shot * flips_per_shot;
+    __syncthreads();
+    for (int o = 0; o < nops; ++o) {
+      const QsTrajOp op = ops[o];
+      if (tid == 0) qs_traj_rows(op, mats, fl, M);
+      fl += 2 * op.k;
+      __syncthreads();
+      qs_traj_apply(state, n, op, M, tid, 256);
+      __syncthreads();
+    }
+    if (out_states)
+      for (uint64_t i = tid; i < dim; i += 256) out_states[(uint64_t)shot * dim + i] = state[i];
+    double fr = 0.0, fi = 0.0;
+    int e = 0;
+    for (uint64_t i = tid; i < dim; i += 256, ++e) {
+      const qs_c128 v = state[i];
+      acc[e] += v.x * v.x + v.y * v.y;
+      if (obs) { const qs_c128 w = obs[i]; fr += w.x * v.x + w.y * v.y; fi += w.x * v.y - w.y * v.x; }
+    }
+    if (obs && out_fid) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        fr += __shfl_down_sync(0xffffffffu, fr, off);
+        fi += __shfl_down_sync(0xffffffffu, fi, off);
+      }
+      if ((tid & 31u) == 0) { red[2 * (tid >> 5)] = fr; red[2 * (tid >> 5) + 1] = fi; }
+      __syncthreads();
+      if (tid == 0) {
+        double sr = 0.0, si = 0.0;
+        for (int w = 0; w < 8; ++w) { sr += red[2 * w]; si += red[2 * w + 1]; }
+        out_fid[shot] = sr * sr + si * si;
+      }
+    }
+    __syncthreads();
+  }
+  if (out_prob) {
+    int e = 0;
+    for (uint64_t i = tid; i < dim; i += 256, ++e) atomicAdd(out_prob + i, acc[e]);
+  }
+}
+
+// =====================================================================================
 // Dense k-qubit block, 5 <= k <= 10 (Gate.apply with any k, DV/gates.py:44-54): in place,
 // one pass over the state, FP64 tensor-core MMA (DMMA.8x8x4)
 // =====================================================================================
@@ -1076,6 +1139,31 @@ int qsim_rb_batch(int nq, int64_t n_seq, const uint16_t* opcodes, const int64_t*
   else
     k_rb_batch<2><<<blocks, 128, 0, st>>>(n_seq, opcodes, offsets, superops, unitaries, rho0, psi0,
                                          out_fidelity, out_purity, out_rho);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QS_CUDA(cudaGetLastError());
+  return QSIM_OK;
+}
+
+int qsim_traj_batch(int n_qubits, int64_t shots, int n_ops, const int32_t* ops, const double* matrices,
+                    const uint8_t* flips, int64_t flips_per_shot, const double* psi0, const double* observable,
+                    double* out_fidelity, double* out_prob_sum, double* out_states, void* stream) {
+  if (!ops || !matrices || !flips || !psi0) return qs::fail(QSIM_ERR_ARG, "qsim_traj_batch: null argument");
+  if (n_qubits < 1 || n_qubits > 12) return qs::fail(QSIM_ERR_UNSUPPORTED, "qsim_traj_batch: 1 <= n_qubits <= 12");
+  if (shots < 0 || n_ops < 0 || flips_per_shot < 0) return qs::fail(QSIM_ERR_ARG, "qsim_traj_batch: bad sizes");
+  if (shots == 0) return QSIM_OK;
+  Bound bound;
+  int rc = bind_device(psi0, &bound);
+  if (rc != QSIM_OK) return rc;
+  const int smem = (int)(sizeof(qs_c128) << n_qubits);
+  if (smem > 48 * 1024) QS_CUDA(cudaFuncSetAttribute(k_traj_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traj_batch, 256, smem));
+  if (occ < 1) return qs::fail(QSIM_ERR_CUDA, "trajectory batch does not fit on an SM");
+  int64_t grid = (int64_t)bound.ctx->sms * occ;
+  if (grid > shots) grid = shots;
+  k_traj_batch<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+      n_qubits, shots, n_ops, (const QsTrajOp*)ops, matrices, flips, flips_per_shot, (const qs_c128*)psi0,
+      (const qs_c128*)observable, out_fidelity, out_prob_sum, (qs_c128*)out_states);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -84,6 +84,24 @@ class CudaBackend:
         dst.copy_(buf.reshape(-1))          # synchronous D2H; pinned `out` runs at link speed
         return out
 
+    def download_async(self, buf, out: np.ndarray):
+        """Start a device-to-host copy into the (pinned) array ``out`` on a side stream, ordered
+        after the work queued so far on the current stream; returns a handle whose ``wait()``
+        blocks until the data has landed.  The compute stream is free at once, so the next
+        circuit can run while this one's result crosses PCIe."""
+        torch = self.torch
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        done = torch.cuda.Event()
+        done.record()
+        dst = torch.from_numpy(out.reshape(-1))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(done)
+            dst.copy_(buf.reshape(-1), non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record()
+        return _PendingCopy(buf, dst, landed)
+
     def clone(self, buf):
         return buf.clone()
 
@@ -101,6 +119,22 @@ class CudaBackend:
         """Pinned host buffer viewed as a complex128 ndarray (for `out=`)."""
         t = self.torch.empty(int(count), dtype=self.torch.complex128, pin_memory=True)
         return t.numpy()
+
+
+class _PendingCopy:
+    """Handle of ``CudaBackend.download_async``: keeps the device buffer alive until the copy
+    has finished."""
+
+    def __init__(self, buf, dst, event):
+        self._buf, self._dst, self._event = buf, dst, event
+
+    def done(self) -> bool:
+        return self._event is None or self._event.query()
+
+    def wait(self) -> None:
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = self._buf = self._dst = None
 
 
 class _StreamPipeline:
@@ -225,6 +259,22 @@ class Plan:
                 pass
 
 
+class PendingState:
+    """Result of a non-blocking run: the final state on its way to a pinned host buffer."""
+
+    def __init__(self, copy, array: np.ndarray):
+        self._copy, self._array = copy, array
+
+    def done(self) -> bool:
+        return self._copy is None or self._copy.done()
+
+    def result(self) -> np.ndarray:
+        if self._copy is not None:
+            self._copy.wait()
+            self._copy = None
+        return self._array
+
+
 # ---- states ------------------------------------------------------------------------------
 class DeviceState:
     """A ket (ndim 1) or density matrix (ndim 2, stored as its row-major vec)
@@ -290,6 +340,17 @@ class DeviceState:
 
     def copy(self) -> "DeviceState":
         return DeviceState(self.backend, self.backend.clone(self.buf), self.n_bits, self.ndim, self.host_dtype)
+
+    def to_numpy_async(self, out: np.ndarray) -> "PendingState":
+        """Start copying the state into the pinned complex128 buffer ``out`` and return at once;
+        ``result()`` of the returned object waits for the copy and gives the array."""
+        if out.dtype != np.complex128 or out.size != (1 << self.n_bits) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous complex128 array of the state's size")
+        start = getattr(self.backend, "download_async", None)
+        if start is None:                                   # host emulator: nothing to overlap
+            self.backend.download(self.buf, out)
+            return PendingState(None, out.reshape(self.shape))
+        return PendingState(start(self.buf, out), out.reshape(self.shape))
 
     def to_numpy(self, out: np.ndarray | None = None, mirror_dtype: bool = True) -> np.ndarray:
         """Copy to the host.  With ``mirror_dtype`` the result is cast to the

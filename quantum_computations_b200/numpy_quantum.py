@@ -212,10 +212,11 @@ def fidelity(a, b) -> float:
     a_ket, b_ket = a.ndim == 1, b.ndim == 1
     if a_ket and b_ket:
         return np.abs(a.conj() @ b).real ** 2
+    # same expressions (hence the same summation order) as the reference, numpy_quantum.py:153-156
     if a_ket:
-        return np.vdot(a, b @ a).real
+        return (a.conj() @ b @ a).real
     if b_ket:
-        return np.vdot(b, a @ b).real
+        return (b.conj() @ a @ b).real
     spectrum = np.clip(np.linalg.eigvals(a @ b).real, 0.0, None)
     return np.sum(np.sqrt(spectrum)) ** 2
 
@@ -223,7 +224,7 @@ def fidelity(a, b) -> float:
 def purity(rho) -> float:
     if _is_device(rho):
         return rho.purity()
-    return np.einsum("ij,ji->", rho, rho).real
+    return np.trace(rho @ rho).real          # the reference's expression (numpy_quantum.py:166)
 
 
 # ---- tensor-product plumbing (numpy_quantum.py:169-258) ------------------------
@@ -235,7 +236,7 @@ def tensor(*arrays):
 
 
 def is_power_of_two(n):
-    return n > 0 and bin(n).count("1") == 1 if isinstance(n, (int, np.integer)) else (n != 0 and (n & (n - 1)) == 0)
+    return (n & (n - 1) == 0) and n != 0
 
 
 def is_qubit_operator(oper):

@@ -120,10 +120,14 @@ class Simulator:
         return plan.stats
 
     # -- public ---------------------------------------------------------------------------
-    def run(self, initial_state=None, *, out: np.ndarray | None = None, return_device: bool = False):
+    def run(self, initial_state=None, *, out: np.ndarray | None = None, return_device: bool = False,
+            block: bool = True):
         """Run the circuit.  Additive keyword arguments: ``out`` (a preallocated,
-        ideally pinned, complex128 host buffer to receive the final state) and
-        ``return_device`` (hand back the ``DeviceState`` without any download)."""
+        ideally pinned, complex128 host buffer to receive the final state),
+        ``return_device`` (hand back the ``DeviceState`` without any download) and
+        ``block=False`` (needs ``out``): return an ``engine.PendingState`` as soon as the work is
+        queued -- the device-to-host copy runs on a side stream, so the next ``run`` computes
+        while this result crosses PCIe; ``.result()`` waits for it."""
         from . import engine
         self.results = []
         self.last_stats = []
@@ -162,4 +166,8 @@ class Simulator:
 
         if return_device:
             return state
+        if not block:
+            if out is None:
+                raise ValueError("block=False needs a preallocated `out` buffer")
+            return state.to_numpy_async(out)
         return state.to_numpy(out=out)

@@ -519,3 +519,130 @@ def check_dm_layers_vs_oracle(backend, n, depth, seed, db=10.0):
     assert err < RTOL, err
     assert abs(np.trace(got).real - 1.0) < 1e-12
     return err
+
+
+# ---- SURVEY section 8f rows, on the device: trajectories (f1), MB layering (f2), Cliffords (f3) ---
+def _oracle_rho(circ, noise, n):
+    """rho after the noisy circuit by the CPU oracle: dense operators and Kraus sums."""
+    rho = np.zeros((2 ** n, 2 ** n), dtype=np.complex128)
+    rho[0, 0] = 1.0
+    for g in circ:
+        rho = dense_ref.apply_matrix(rho, g.indices, g.matrix)
+        for q, (px, pz) in zip(g.indices, noise.flips_for(g)):
+            rho = dense_ref.apply_kraus(rho, [q], gkp_noise.pauli_flip_kraus(px, pz))
+    return rho
+
+
+def check_trajectories(backend, shots=4000):
+    """f1: the batched Pauli-trajectory executor (qsim_traj_batch).
+    (1) deterministic: every shot's ket equals the CPU oracle's run of the circuit with that
+        shot's X / Z flips inserted as gates;
+    (2) the batched and the shot-by-shot path draw the same trajectories from one seed;
+    (3) statistical: the shot average converges to the ORACLE's density matrix (4 sigma)."""
+    from quantum_computations_b200 import trajectories
+    noise = channels.GKPNoise(7.0)                       # strong noise: errors in most shots
+    n = 4
+    circ = [gates.H(0), gates.CZ(0, 1), gates.T(1), gates.H(1), gates.CZ(1, 2), gates.P(2), gates.H(2),
+            gates.SWAP(0, 2), gates.H(0), gates.CX(3, 1), gates.RZ(3, 0.37), gates.H(3), gates.CZ(3, 0), gates.Tdg(2)]
+    psi0 = np.zeros(2 ** n, dtype=np.complex128)
+    psi0[0] = 1.0
+    ideal, _ = strided.run(as_oracle_ops(circ), psi0)
+    # (1)
+    rng = np.random.default_rng(5)
+    flips = trajectories.sample_flips(circ, noise, 24, rng)
+    res = trajectories.run_batch(circ, flips, psi0, backend=backend, observable=ideal, return_states=True)
+    assert flips.any()
+    for s in range(flips.shape[0]):
+        explicit, col = [], 0
+        for g in circ:
+            explicit.append(g)
+            for q in g.indices:
+                if flips[s, col]:
+                    explicit.append(gates.X(q))
+                if flips[s, col + 1]:
+                    explicit.append(gates.Z(q))
+                col += 2
+        ref, _ = strided.run(as_oracle_ops(explicit), psi0)
+        assert rel_err(res["states"][s], ref) < RTOL, s
+        assert abs(res["fidelities"][s] - abs(np.vdot(ideal, ref)) ** 2) < 1e-12
+    # (2)
+    a = trajectories.run_trajectories(circ, noise, [State.ZERO] * n, 12, np.random.default_rng(9), backend=backend,
+                                      observable=ideal, batch=True)
+    b = trajectories.run_trajectories(circ, noise, [State.ZERO] * n, 12, np.random.default_rng(9), backend=backend,
+                                      observable=ideal, batch=False)
+    assert np.abs(a["probabilities"] - b["probabilities"]).max() < 1e-12 and abs(a["fidelity"] - b["fidelity"]) < 1e-12
+    # (3)
+    rho = _oracle_rho(circ, noise, n)
+    res = trajectories.run_trajectories(circ, noise, [State.ZERO] * n, shots, np.random.default_rng(7),
+                                        backend=backend, observable=ideal)
+    want_p = np.real(np.diagonal(rho))
+    want_f = float(np.real(np.vdot(ideal, rho @ ideal)))
+    tol = 4.0 * 0.5 / np.sqrt(shots)                      # binomial standard error <= 0.5 / sqrt(shots)
+    assert np.max(np.abs(res["probabilities"] - want_p)) < tol
+    assert abs(res["fidelity"] - want_f) < tol
+    assert abs(res["probabilities"].sum() - 1.0) < 1e-12
+
+
+def check_layered_noise(backend):
+    """f2: a circuit scheduled into measurement-based layers (idle qubits charged with identity
+    steps, Pauli gates as byproducts) and simulated with the per-layer GKP channel, against
+    the CPU oracle's Kraus sums on the same scheduled circuit."""
+    from quantum_computations_b200 import layering
+    noise = channels.GKPNoise(9.0)
+    n = 4
+    circ = [gates.H(0), gates.CZ(0, 1), gates.X(2), gates.H(2), gates.T(3), gates.CZ(2, 3), gates.P(1),
+            gates.SWAP(1, 2), gates.H(3), gates.Pdg(0), gates.CZ(0, 1), gates.H(1)]
+    noisy = layering.noisy_circuit(circ, noise, n)
+    lay = layering.MBLayering.of(circ, n)
+    assert lay.depth() >= 4
+    rho0 = np.zeros((2 ** n, 2 ** n), dtype=np.complex128)
+    rho0[0, 0] = 1.0
+    got = Simulator(noisy, backend=backend).run(rho0)
+    ref, _ = strided.run(as_oracle_ops(noisy), rho0)
+    assert rel_err(got, ref) < RTOL
+    assert abs(np.trace(got).real - 1.0) < 1e-12
+
+
+def check_clifford_rb(backend):
+    """f3: uniform two-qubit Clifford RB (720 classes mod Paulis) through the batched executor:
+    the inverse brings |00> back exactly; with the GKP channel the survival decays to 1/4;
+    single sequences agree with the CPU oracle."""
+    from quantum_computations_b200 import cliffords
+    rng = np.random.default_rng(11)
+    seqs = cliffords.clifford_rb_sequences(40, 6, rng)
+    clean = BatchedSimulator(2, None, backend=backend).run(seqs)
+    assert np.allclose(clean["fidelity"], 1.0, atol=1e-12)
+    noise = channels.GKPNoise(6.0)
+    noisy = BatchedSimulator(2, noise, backend=backend).run(seqs)
+    for i in (0, 7, 23):
+        rho = _oracle_rho(seqs[i], noise, 2)
+        psi = np.array([1, 0, 0, 0], dtype=np.complex128)
+        for g in seqs[i]:
+            psi = dense_ref.apply_matrix(psi, g.indices, g.matrix)
+        assert abs(noisy["fidelity"][i] - dense_ref.fidelity(rho, psi)) < 1e-12
+        assert abs(noisy["purity"][i] - dense_ref.purity(rho)) < 1e-12
+    long_seqs = cliffords.clifford_rb_sequences(40, 40, rng)
+    f_long = BatchedSimulator(2, noise, backend=backend).run(long_seqs)["fidelity"].mean()
+    assert abs(f_long - 0.25) < 0.03                                  # PAPER/plot_data.ipynb:188-189 asymptote
+
+
+def check_nonblocking_run(backend):
+    """Simulator.run(..., out=pinned, block=False): results of overlapping calls land in their own
+    buffers and equal the blocking result."""
+    n = 12
+    circ = workloads.sv_random_circuit(n, 3, 5)
+    sim = Simulator(circ, backend=backend)
+    want = sim.run([State.ZERO] * n)
+    outs = [backend.pinned_empty(1 << n) for _ in range(3)]
+    pending = [sim.run([State.ZERO] * n, out=o, block=False) for o in outs]
+    for p, o in zip(pending, outs):
+        got = p.result()
+        assert got is not None and np.shares_memory(got, o)
+        assert rel_err(got, want) < 1e-15
+        assert p.done()
+    try:
+        sim.run([State.ZERO] * n, block=False)
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("block=False without out must raise")

@@ -73,3 +73,19 @@ def test_deferred_tails(emu_backend):
 def test_dm_layers(emu_backend):
     pc.check_dm_layers_vs_oracle(emu_backend, n=4, depth=6, seed=12)
     pc.check_dm_layers_vs_oracle(emu_backend, n=6, depth=3, seed=12)
+
+
+def test_trajectories_batched(emu_backend):
+    pc.check_trajectories(emu_backend, shots=3000)
+
+
+def test_layered_noise(emu_backend):
+    pc.check_layered_noise(emu_backend)
+
+
+def test_clifford_rb(emu_backend):
+    pc.check_clifford_rb(emu_backend)
+
+
+def test_nonblocking_run(emu_backend):
+    pc.check_nonblocking_run(emu_backend)

@@ -159,3 +159,22 @@ def test_circuit_then_inverse_returns_zero_state(cuda_backend, n):
     assert abs(out.buf[0].item() - 1.0) < 1e-10
     rest = torch.linalg.vector_norm(out.buf[1:]).item()
     assert rest < 1e-10
+
+
+def test_trajectories_batched(cuda_backend):
+    """SURVEY 8f rank 1 on the device, against the CPU oracle."""
+    pc.check_trajectories(cuda_backend, shots=20000)
+
+
+def test_layered_noise(cuda_backend):
+    """SURVEY 8f rank 2 on the device, against the CPU oracle."""
+    pc.check_layered_noise(cuda_backend)
+
+
+def test_clifford_rb(cuda_backend):
+    """SURVEY 8f rank 3 on the device, against the CPU oracle."""
+    pc.check_clifford_rb(cuda_backend)
+
+
+def test_nonblocking_run(cuda_backend):
+    pc.check_nonblocking_run(cuda_backend)
