@@ -505,3 +505,26 @@ int qsim_emu_plan_shape(const qsim_plan_t* p, int* out, int max_passes) {
 }
 
 }  // extern "C"
+
+// Test-only: byte offsets (inside the tile) that the 32 lanes of `warp` touch in the
+// 128-bit access of amplitude m, iteration i, of step s of pass `pass_no` (0-based).
+extern "C" int qsim_emu_step_lane_bytes(const qsim_plan_t* p, int pass_no, int s, int warp, int i, int m, int* out) {
+  if (!p || !out) return -1;
+  int k = 0;
+  for (const qs::PlanItem& it : p->items) {
+    if (it.generic) continue;
+    if (k++ != pass_no) continue;
+    const QsPass& P = it.pass;
+    if (s >= (int)P.nsteps) return -2;
+    const QsStep& st = P.steps[s];
+    QsStepTab tab;
+    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, QS_THREADS_LOG2);
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t tid = (uint32_t)warp * 32u + (uint32_t)l;
+      const uint32_t slo = qs_swz(qs_thread_jlo(tab, tid));
+      out[l] = (int)((((slo ^ (st.hi[i] >> 16)) << 4) ^ st.sdepb[m]));
+    }
+    return (int)st.r;
+  }
+  return -3;
+}
