@@ -528,3 +528,28 @@ extern "C" int qsim_emu_step_lane_bytes(const qsim_plan_t* p, int pass_no, int s
   }
   return -3;
 }
+
+// Test-only: print the shape of every pass of a plan (tile bits, steps, layers).
+extern "C" int qsim_emu_plan_describe(const qsim_plan_t* p) {
+  if (!p) return -1;
+  int k = 0;
+  for (const qs::PlanItem& it : p->items) {
+    if (it.generic) { fprintf(stderr, "item %d: generic k=%d\n", k++, it.op.k); continue; }
+    const QsPass& P = it.pass;
+    fprintf(stderr, "pass %d: T=%u steps=%u layers=%u coef=%u pairs=%u final=%d tile_bits", k++, P.T, P.nsteps, P.nlayers,
+            P.ncoef, P.npairs, P.has_final);
+    for (uint32_t l = 0; l < P.T; ++l) fprintf(stderr, " %d", P.tile_bits[l]);
+    fprintf(stderr, "\n");
+    for (uint32_t s = 0; s < P.nsteps; ++s) {
+      const QsStep& st = P.steps[s];
+      fprintf(stderr, "   step %u: r=%d layers %d..%d sync=%d gpos", s, st.r, st.layer0, st.layer0 + st.nlayers - 1, st.block_sync);
+      for (int f = 0; f < st.r; ++f) fprintf(stderr, " %d", st.gpos[f]);
+      fprintf(stderr, " fpos");
+      for (int f = 0; f < (int)P.T - st.r; ++f) fprintf(stderr, " %d", st.fpos[f]);
+      fprintf(stderr, " kinds");
+      for (int l = st.layer0; l < st.layer0 + st.nlayers; ++l) fprintf(stderr, " %d/%x", P.layers[l].kind, P.layers[l].flags);
+      fprintf(stderr, "\n");
+    }
+  }
+  return k;
+}
