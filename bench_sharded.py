@@ -144,7 +144,8 @@ def run_sharded(args, world, rank, local_rank):
                                 "share_of_step": swap_ms * swaps / ms_per_step,
                                 "note": "one exchange = k rank qubits <-> k local qubits, all 2^k - 1 blocks in ONE "
                                         "kernel per rank over peer memory (1 - 2^-k of the shard leaves each GPU); "
-                                        "CUDA events around barrier + kernel + barrier, max over ranks"},
+                                        "CUDA events from behind the barrier that starts the exchange (all ranks have finished their "
+                                        "passes) to behind the barrier that ends it, max over ranks"},
             "check": check, "secondary": [rb] if rb else [], "cpu_baseline": None,
             "e2e": {"value": raw, "unit": "gates/s",
                     "h2d_bytes_per_step": PASS_PARAM_BYTES * passes + 64 * n, "d2h_bytes_per_step": 16,

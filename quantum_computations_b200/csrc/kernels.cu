@@ -441,32 +441,47 @@ struct ExchGeom {
 };
 constexpr int kExchSplitBit = 5;
 
+// U pairs per thread and trip: all 2 U loads (U of them over NVLink) are issued before the
+// first store, which is what keeps enough bytes in flight to cover the NVLink round trip.
+template <int U>
 __global__ void __launch_bounds__(256)
 k_exchange_p2p(qs_c128* __restrict__ shard, const __grid_constant__ ExchGeom G) {
   const int k = G.k;
   const uint64_t half = 1ull << (G.n_local - k - 1);          // amplitudes per partner that THIS rank moves
   const uint64_t total = half * ((1ull << k) - 1ull);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += stride) {
-    const int d = 1 + (int)(w / half);
-    const uint64_t q = w % half;
-    // r: index inside the block; bit kExchSplitBit says which of the two ranks moves it
-    const uint64_t low = q & ((1ull << kExchSplitBit) - 1ull);
-    const uint64_t r = ((q >> kExchSplitBit) << (kExchSplitBit + 1)) | ((uint64_t)G.higher[d] << kExchSplitBit) | low;
-    uint64_t mine_idx = r, theirs_idx = r;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+  for (uint64_t w0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; w0 < total; w0 += stride) {
+    qs_c128* mine[U];
+    qs_c128* remote[U];
+    qs_c128 x[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint64_t w = w0 + (uint64_t)u * blockDim.x;
+      mine[u] = nullptr;
+      if (w >= total) continue;
+      const int d = 1 + (int)(w / half);
+      const uint64_t q = w % half;
+      // r: index inside the block; bit kExchSplitBit says which of the two ranks moves it
+      const uint64_t low = q & ((1ull << kExchSplitBit) - 1ull);
+      const uint64_t r = ((q >> kExchSplitBit) << (kExchSplitBit + 1)) | ((uint64_t)G.higher[d] << kExchSplitBit) | low;
+      uint64_t mine_idx = r, theirs_idx = r;
 #pragma unroll 1
-    for (int i = 0; i < k; ++i) {
-      const uint64_t lo_m = mine_idx & ((1ull << G.pos[i]) - 1ull);
-      const uint64_t lo_t = theirs_idx & ((1ull << G.pos[i]) - 1ull);
-      const uint64_t vd = (uint64_t)(G.mine[i] ^ ((d >> i) & 1));    // partner's rank bit
-      mine_idx = ((mine_idx >> G.pos[i]) << (G.pos[i] + 1)) | (vd << G.pos[i]) | lo_m;
-      theirs_idx = ((theirs_idx >> G.pos[i]) << (G.pos[i] + 1)) | ((uint64_t)G.mine[i] << G.pos[i]) | lo_t;
+      for (int i = 0; i < k; ++i) {
+        const uint64_t lo_m = mine_idx & ((1ull << G.pos[i]) - 1ull);
+        const uint64_t lo_t = theirs_idx & ((1ull << G.pos[i]) - 1ull);
+        const uint64_t vd = (uint64_t)(G.mine[i] ^ ((d >> i) & 1));    // partner's rank bit
+        mine_idx = ((mine_idx >> G.pos[i]) << (G.pos[i] + 1)) | (vd << G.pos[i]) | lo_m;
+        theirs_idx = ((theirs_idx >> G.pos[i]) << (G.pos[i] + 1)) | ((uint64_t)G.mine[i] << G.pos[i]) | lo_t;
+      }
+      mine[u] = shard + mine_idx;
+      remote[u] = G.peer[d] + theirs_idx;
     }
-    qs_c128* remote = G.peer[d] + theirs_idx;
-    const qs_c128 x = shard[mine_idx];
-    const qs_c128 y = *remote;
-    *remote = x;
-    shard[mine_idx] = y;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (mine[u]) { y[u] = *remote[u]; x[u] = *mine[u]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (mine[u]) { *remote[u] = x[u]; *mine[u] = y[u]; }
   }
 }
 
@@ -935,10 +950,19 @@ int qsim_exchange_p2p(void* shard, void* const* peer_shards, int n_local, int nb
   int rc = bind_device(shard, &bound);
   if (rc != QSIM_OK) return rc;
   const uint64_t total = (1ull << (n_local - nbits - 1)) * ((1ull << nbits) - 1ull);
-  uint64_t blocks = (total + 255) / 256;
-  const uint64_t cap = (uint64_t)bound.ctx->sms * 8;
+  // development knobs (defaults measured on 2 and 8 B200s): pairs per thread and trip, CTAs per SM
+  static const int batch = [] { const char* e = getenv("QSIM_EXCH_BATCH"); return e ? atoi(e) : 4; }();
+  static const int per_sm = [] { const char* e = getenv("QSIM_EXCH_CTAS"); return e ? atoi(e) : 8; }();
+  const int U = batch >= 8 ? 8 : batch >= 4 ? 4 : batch >= 2 ? 2 : 1;
+  uint64_t blocks = (total + 256ull * U - 1) / (256ull * U);
+  const uint64_t cap = (uint64_t)bound.ctx->sms * (uint64_t)(per_sm > 0 ? per_sm : 8);
   if (blocks > cap) blocks = cap;
-  k_exchange_p2p<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((qs_c128*)shard, G);
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (U == 8) k_exchange_p2p<8><<<(unsigned)blocks, 256, 0, st>>>((qs_c128*)shard, G);
+  else if (U == 4) k_exchange_p2p<4><<<(unsigned)blocks, 256, 0, st>>>((qs_c128*)shard, G);
+  else if (U == 2) k_exchange_p2p<2><<<(unsigned)blocks, 256, 0, st>>>((qs_c128*)shard, G);
+  else k_exchange_p2p<1><<<(unsigned)blocks, 256, 0, st>>>((qs_c128*)shard, G);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

@@ -290,7 +290,9 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
       }
       if (DENSE && (head & QS_LH_DENSE)) {
         // dense 2^R x 2^R matrix: inputs are all in registers, so rows can be
-        // written back one at a time (rolled loop keeps the code small)
+        // written back one at a time (4x4: unrolled, the coefficients become uniform operands;
+        // larger: a rolled loop keeps the code small)
+        constexpr int ROW_UNROLL = R <= 2 ? NA : 1;
         const double* mat = P.coef + (H.offs & 0xffffu);
         // the only layer that may follow a dense one is the pass's final sign layer
         uint32_t S2[NA];
@@ -303,7 +305,7 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
         uint32_t sg2 = 0u;               // bit `row` set: negate that output (a rolled loop cannot index S2)
 #pragma unroll
         for (int m = 0; m < NA; ++m) sg2 |= (S2[m] >> 31) << m;
-#pragma unroll 1
+#pragma unroll ROW_UNROLL
         for (int row = 0; row < NA; ++row) {
           double re = 0.0, im = 0.0;
 #pragma unroll

@@ -275,8 +275,8 @@ class ShardedState:
             lower[d] = 1 if partner < self.comm.rank else 0
         my_bits = (C.c_int * k)(*mine)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
         self._rank_barrier(p2p["token"])           # every rank has finished the passes before the exchange
+        ev0.record()                               # (waiting for the slowest rank's passes is not exchange time)
         _capi.check(lib, lib.qsim_exchange_p2p(be.ptr(self.buf), peers, self.n_local, k, qubits, my_bits, lower,
                                                be.stream()))
         self._rank_barrier(p2p["token"])           # every rank's kernel is done: the shards are whole again
