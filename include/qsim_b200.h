@@ -50,6 +50,10 @@ typedef struct {
                                caller can merge them into its next plan (needs merge_1q on)      */
   int32_t max_layers;       /* gate layers per shared-memory round trip (1..8): a qubit whose
                                amplitudes are in registers can take its next gates there;  0 = default */
+  int32_t cta_log2;         /* log2 threads per CTA of the tile pass: 7 or 8; 0 = chosen per pass (small CTAs,
+                               three to an SM, for passes with many gates; large ones for passes that
+                               are bound by HBM)                                                        */
+  int32_t reserved0;        /* must be 0 */
   uint64_t apply_tail_mask; /* with defer_tail: qubits (bit q = qubit q) whose trailing products are
                                applied all the same                                              */
 } qsim_plan_options_t;

@@ -23,6 +23,8 @@ class PlanOptions(C.Structure):
         ("merge_1q", C.c_int32),
         ("defer_tail", C.c_int32),
         ("max_layers", C.c_int32),
+        ("cta_log2", C.c_int32),
+        ("reserved0", C.c_int32),
         ("apply_tail_mask", C.c_uint64),
     ]
 

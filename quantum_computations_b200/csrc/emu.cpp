@@ -30,12 +30,13 @@ int64_t g_launches = 0;
 int g_ownership_violations = 0;
 
 void slots_of_step(const QsPass& P, int s, const QsStepTab& tab, std::vector<int>& owner) {
+  const uint32_t nthreads = 1u << P.cta_log2;
   const QsStep& st = P.steps[s];
   const uint32_t nwork = 1u << (P.T - st.r);
   owner.assign((size_t)1 << P.T, -1);
-  for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
+  for (uint32_t tid = 0; tid < nthreads; ++tid) {
     const uint32_t jlo = qs_thread_jlo(tab, tid);
-    for (uint32_t i = 0, w = tid; w < nwork; ++i, w += QS_THREADS) {
+    for (uint32_t i = 0, w = tid; w < nwork; ++i, w += nthreads) {
       const uint32_t j0 = jlo | (st.hi[i] & 0xffffu);
       for (int m = 0; m < (1 << st.r); ++m) {
         uint32_t d = 0;
@@ -64,6 +65,8 @@ void check_warp_ownership(const QsPass& P, int s, const QsStepTab& tab_s) {
 }
 
 void emu_pass(const QsPass& P, qs_c128* state, int n) {
+  const uint32_t nthreads = 1u << P.cta_log2;
+  const uint32_t thr_log2 = P.cta_log2;
   const uint64_t ntiles = 1ull << (n - (int)P.T);
   const int nsteps = (int)P.nsteps;
   std::vector<qs_c128> tile((size_t)1 << P.T);
@@ -72,26 +75,26 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
   bool dense = false;
   for (uint32_t l = 0; l < P.nlayers; ++l) dense |= P.layers[l].kind == QS_LAYER_DENSE;
   for (int s = 0; s < nsteps; ++s)
-    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab[s], QS_THREADS_LOG2);
-  std::vector<uint32_t> fin_qlo(QS_THREADS, 0);
+    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab[s], thr_log2);
+  std::vector<uint32_t> fin_qlo(nthreads, 0);
   if (P.has_final)
-    for (uint32_t tid = 0; tid < QS_THREADS; ++tid)
+    for (uint32_t tid = 0; tid < nthreads; ++tid)
       fin_qlo[tid] = qs_fin_quad(P, qs_thread_jlo(tab[nsteps - 1], tid));
   for (uint64_t t = 0; t < ntiles; ++t) {
     const uint64_t base = qs_tile_base(P, t);
     for (int l = 0; l < (int)P.nlayers; ++l)
       zm[l] = (P.layers[l].flags & QS_LF_SIGN) ? qs_layer_z(P, l, base) : 0u;
     const uint32_t fin_g = P.has_final ? qs_fin_g(P, base) : 0u;
-    for (uint32_t tid = 0; tid < QS_THREADS; ++tid) qs_plain_load(P, state, tile.data(), base, tid, QS_THREADS);
+    for (uint32_t tid = 0; tid < nthreads; ++tid) qs_plain_load(P, state, tile.data(), base, tid, nthreads);
     for (int s = 0; s < nsteps; ++s) {
-      for (uint32_t tid = 0; tid < QS_THREADS; ++tid) {
+      for (uint32_t tid = 0; tid < nthreads; ++tid) {
         // same variant selection as launch_pass() in kernels.cu
-        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, QS_THREADS_LOG2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
-        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, QS_THREADS_LOG2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
       }
       if (t == 0) check_warp_ownership(P, s, tab[s]);
     }
-    for (uint32_t tid = 0; tid < QS_THREADS; ++tid) qs_plain_store(P, state, tile.data(), base, tid, QS_THREADS);
+    for (uint32_t tid = 0; tid < nthreads; ++tid) qs_plain_store(P, state, tile.data(), base, tid, nthreads);
   }
   ++g_launches;
 }
@@ -452,16 +455,17 @@ int qsim_emu_step_wavefronts(const qsim_plan_t* p, double* out) {
       const double t_before = total, i_before = ideal;
       const QsStep& st = P.steps[s];
       QsStepTab tab;
-      for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, QS_THREADS_LOG2);
+      const uint32_t nthreads = 1u << P.cta_log2;
+      for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, P.cta_log2);
       const uint32_t nwork = 1u << (P.T - st.r);
-      for (uint32_t warp = 0; warp < QS_THREADS / 32; ++warp)
-        for (uint32_t i = 0, w0 = warp * 32; w0 < nwork; ++i, w0 += QS_THREADS)
+      for (uint32_t warp = 0; warp < nthreads / 32; ++warp)
+        for (uint32_t i = 0, w0 = warp * 32; w0 < nwork; ++i, w0 += nthreads)
           for (int m = 0; m < (1 << st.r); ++m)
             for (int quarter = 0; quarter < 4; ++quarter) {
               int count[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
               for (int l = 0; l < 8; ++l) {
                 const uint32_t tid = warp * 32 + quarter * 8 + l;
-                if (tid + i * QS_THREADS >= nwork) continue;
+                if (tid + i * nthreads >= nwork) continue;
                 const uint32_t jlo = qs_thread_jlo(tab, tid);
                 const uint32_t slo = qs_swz(jlo);
                 const uint32_t byte = ((slo ^ (st.hi[i] >> 16)) << 4) ^ st.sdepb[m];
@@ -518,7 +522,7 @@ extern "C" int qsim_emu_step_lane_bytes(const qsim_plan_t* p, int pass_no, int s
     if (s >= (int)P.nsteps) return -2;
     const QsStep& st = P.steps[s];
     QsStepTab tab;
-    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, QS_THREADS_LOG2);
+    for (int e = 0; e < QS_TAB_ENTRIES; ++e) qs_build_step_tab(P, s, e, &tab, P.cta_log2);
     for (int l = 0; l < 32; ++l) {
       const uint32_t tid = (uint32_t)warp * 32u + (uint32_t)l;
       const uint32_t slo = qs_swz(qs_thread_jlo(tab, tid));

@@ -39,7 +39,7 @@ struct DevCtx {
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
   std::mutex occ_lock;
-  int occ[4] = {0, 0, 0, 0};      // resident CTAs/SM of the k_tile_pass variants at the last smem size
+  int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
 
@@ -149,8 +149,10 @@ __device__ __forceinline__ void tma_box_coords(const QsPass& P, const QsTmaGeom&
 // tile into shared memory (one mbarrier per CTA), the steps run on it, TMA writes it back.
 // The three CTAs of an SM are in different phases, so one CTA's fill and drain overlap
 // the steps of the other two.
-template <int MAXR, bool DENSE>
-__global__ void __launch_bounds__(QS_THREADS, (QS_THREADS_LOG2 >= 9 ? (MAXR <= 3 ? 2 : 1) : (MAXR <= 3 ? 3 : 2)))
+// TL2 = log2 threads per CTA (QsPass::cta_log2): 128-thread CTAs run three (smem-limited) or four
+// to an SM, 256-thread CTAs two (16 amplitudes per thread) or three (8 per thread).
+template <int MAXR, bool DENSE, int TL2>
+__global__ void __launch_bounds__(1 << TL2, (TL2 == 7 ? (MAXR <= 3 ? 6 : 4) : (MAXR <= 3 ? 3 : 2)))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_constant__ CUtensorMap tmap,
             const __grid_constant__ QsTmaGeom G, uint64_t ntiles) {
   extern __shared__ __align__(1024) unsigned char qs_smem[];
@@ -164,8 +166,8 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_const
   const bool use_tma = G.use_tma != 0;
 
   // tile-independent thread tables, once per launch (the grid is persistent)
-  for (int e = (int)tid; e < nsteps * QS_TAB_ENTRIES; e += QS_THREADS)
-    qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], QS_THREADS_LOG2);
+  for (int e = (int)tid; e < nsteps * QS_TAB_ENTRIES; e += (1 << TL2))
+    qs_build_step_tab(P, e / QS_TAB_ENTRIES, e % QS_TAB_ENTRIES, &s_tab[e / QS_TAB_ENTRIES], TL2);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +193,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_const
         }
       }
     } else {
-      qs_plain_load(P, state, tile, base, tid, QS_THREADS);
+      qs_plain_load(P, state, tile, base, tid, (1u << TL2));
     }
     // per-tile sign data, one thread per layer (warps 1 and 2)
     if (tid >= 32 && (int)tid < 32 + nlayers) {
@@ -207,7 +209,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_const
     }
     const uint32_t fin_g = s_zm[QS_MAX_LAYERS];
     for (int s = 0; s < nsteps; ++s) {
-      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, QS_THREADS_LOG2, s_zm, fin_g, fin_qlo, s_tab[s]);
+      qs_phase_step_any<MAXR, DENSE>(P, s, tile, tid, TL2, s_zm, fin_g, fin_qlo, s_tab[s]);
       // the tile goes back through the async proxy: order this thread's writes before it
       if (s == nsteps - 1 && use_tma) fence_async_smem();
       // inside a run the next step touches only amplitudes of the same warp (plan.h)
@@ -224,7 +226,7 @@ k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_const
         tma_commit();
       }
     } else {
-      qs_plain_store(P, state, tile, base, tid, QS_THREADS);
+      qs_plain_store(P, state, tile, base, tid, (1u << TL2));
       __syncthreads();
     }
   }
@@ -321,16 +323,20 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   bool dense = false;
   for (uint32_t s = 0; s < P.nsteps; ++s) maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
   for (uint32_t l = 0; l < P.nlayers; ++l) dense |= P.layers[l].kind == QS_LAYER_DENSE;
-  static const TileKernel variants[4] = {k_tile_pass<3, false>, k_tile_pass<3, true>,
-                                         k_tile_pass<4, false>, k_tile_pass<4, true>};
-  const int vi = (maxr <= 3 ? 0 : 2) + (dense ? 1 : 0);
+  static const TileKernel variants[8] = {
+      k_tile_pass<3, false, 8>, k_tile_pass<3, true, 8>, k_tile_pass<4, false, 8>, k_tile_pass<4, true, 8>,
+      k_tile_pass<3, false, 7>, k_tile_pass<3, true, 7>, k_tile_pass<4, false, 7>, k_tile_pass<4, true, 7>};
+  if (P.cta_log2 != QS_THREADS_LOG2_MIN && P.cta_log2 != QS_THREADS_LOG2)
+    return qs::fail(QSIM_ERR_ARG, "pass built for an unsupported CTA size");
+  const int threads = 1 << P.cta_log2;
+  const int vi = (P.cta_log2 == QS_THREADS_LOG2 ? 0 : 4) + (maxr <= 3 ? 0 : 2) + (dense ? 1 : 0);
   int occ;
   {
     std::lock_guard<std::mutex> guard(ctx->occ_lock);
     if (ctx->occ_smem != smem) {
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < 8; ++v) {
         QS_CUDA(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], QS_THREADS, smem));
+        QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], v < 4 ? 256 : 128, smem));
       }
       ctx->occ_smem = smem;
     }
@@ -342,7 +348,7 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   QsTmaGeom geom;
   CUtensorMap map;
   make_tma_geom(P, state, n, &geom, &map);
-  variants[vi]<<<(unsigned)grid, QS_THREADS, smem, stream>>>(state, P, map, geom, ntiles);
+  variants[vi]<<<(unsigned)grid, threads, smem, stream>>>(state, P, map, geom, ntiles);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QS_CUDA(cudaGetLastError());
   return QSIM_OK;

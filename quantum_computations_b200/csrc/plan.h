@@ -56,13 +56,15 @@
 #define QS_MAX_LAYERS   40     // layers per pass
 #define QS_MAX_PAIRS    640    // (outer,outer) and (local,outer) sign pairs per pass
 #define QS_MAX_COEF     2560   // doubles of coefficients per pass
+// Threads per CTA are chosen per pass (QsPass::cta_log2): 128 or 256.  QS_THREADS_LOG2 is the
+// larger of the two (array sizes, default).
 #ifndef QS_THREADS_LOG2
-#define QS_THREADS_LOG2 8      // threads per CTA = 256
+#define QS_THREADS_LOG2 8
 #endif
+#define QS_THREADS_LOG2_MIN 7
 // largest tile: 2^13 amplitudes = 128 KiB; a step's per-thread iteration table has 16 entries
 #define QS_MAX_T        (QS_THREADS_LOG2 + 5 < 13 ? QS_THREADS_LOG2 + 5 : 13)
 #define QS_THREADS      (1 << QS_THREADS_LOG2)
-#define QS_WARP_BITS    (QS_THREADS_LOG2 - 5)                 // thread-id bits that select the warp
 #define QS_MAX_ITER     (1 << (QS_MAX_T - QS_THREADS_LOG2))   // amplitudes per thread in a plain load/store
 #define QS_MAX_WORK     16                                    // work items per thread and step (r >= 1)
 
@@ -137,7 +139,7 @@ struct QsPass {
   uint8_t  tile_bits[16];        // ascending global bit numbers of the local positions
   // final layer: the part of its sign that is common to a work item
   uint8_t  has_final;            // the last layer of the last step is a QS_LF_FINAL layer
-  uint8_t  pad0;
+  uint8_t  cta_log2;             // log2 threads per CTA this pass's thread maps are built for (7 or 8)
   uint16_t fin_pair_off;         // first pair: fin_n_oo (outer, outer), then the layer's own (local, outer)
   uint16_t fin_n_oo;
   uint16_t fin_qhi;              // bit i: Q(jhi_i) for the last step's iteration i

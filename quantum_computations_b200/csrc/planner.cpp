@@ -37,6 +37,7 @@ qsim_plan_options_t resolve_options(const qsim_plan_options_t* opt) {
   if (o.merge_1q <= 0) o.merge_1q = 1;
   if (o.max_layers <= 0) o.max_layers = 4;
   if (o.max_layers > 8) o.max_layers = 8;
+  if (o.cta_log2 != QS_THREADS_LOG2_MIN && o.cta_log2 != QS_THREADS_LOG2) o.cta_log2 = 0;     // 0: per pass
   if (o.defer_tail != 1 || o.merge_1q != 1) o.defer_tail = 0;
   if (o.tile_bits > QS_MAX_T) o.tile_bits = QS_MAX_T;
   if (o.max_group > QS_MAX_R) o.max_group = QS_MAX_R;
@@ -799,6 +800,8 @@ void order_free_positions(QsStep& st, int T, const int* warp_pos, int nwarp) {
 void assign_runs(QsPass& P) {
   const int T = (int)P.T;
   const int nsteps = (int)P.nsteps;
+  const int thr_log2 = (int)P.cta_log2;
+  const int warp_bits = thr_log2 - 5;            // thread-id bits that select the warp
   auto group_mask = [&](int i) {
     uint32_t g = 0;
     for (int f = 0; f < P.steps[i].r; ++f) g |= 1u << P.steps[i].gpos[f];
@@ -820,19 +823,20 @@ void assign_runs(QsPass& P) {
     int cand[QS_MAX_T], nc = 0;
     for (int p = T - 1; p >= 0; --p)
       if (!(used >> p & 1)) cand[nc++] = p;
-    if (nc < QS_WARP_BITS) return -1;
-    if (QS_WARP_BITS != 3) {
-      for (int i = 0; i < QS_WARP_BITS; ++i) wp[i] = cand[i];
-      return 0;
-    }
+    if (nc < warp_bits) return -1;
     int best = -1;
+    // every choice of warp_bits (2 or 3) candidates
     for (int a = 0; a < nc; ++a)
       for (int b = a + 1; b < nc; ++b)
-        for (int c = b + 1; c < nc; ++c) {
-          const uint32_t wmask = (1u << cand[a]) | (1u << cand[b]) | (1u << cand[c]);
+        for (int c = (warp_bits == 3 ? b + 1 : nc - 1); c < nc; ++c) {
+          uint32_t wmask = (1u << cand[a]) | (1u << cand[b]);
+          if (warp_bits == 3) wmask |= 1u << cand[c];
           int ok = 0;
           for (int i = s; i < e; ++i) ok += lanes_ok(i, wmask) ? 1 : 0;
-          if (ok > best) { best = ok; wp[0] = cand[a]; wp[1] = cand[b]; wp[2] = cand[c]; }
+          if (ok > best) {
+            best = ok; wp[0] = cand[a]; wp[1] = cand[b];
+            if (warp_bits == 3) wp[2] = cand[c];
+          }
         }
     return best;
   };
@@ -847,7 +851,7 @@ void assign_runs(QsPass& P) {
     while (e < nsteps) {
       const uint32_t u = used | group_mask(e);
       const int r = std::max(maxr, (int)P.steps[e].r);
-      if (T - __builtin_popcount(u) < QS_WARP_BITS || T - r < QS_THREADS_LOG2) break;
+      if (T - __builtin_popcount(u) < warp_bits || T - r < thr_log2) break;
       int trial[4];
       const int ok = best_warp_positions(s, e + 1, u, trial);
       const int want = can_ok + (lanes_ok(e, 0) ? 1 : 0);
@@ -855,7 +859,7 @@ void assign_runs(QsPass& P) {
       used = u;
       maxr = r;
       can_ok = want;
-      for (int i = 0; i < QS_WARP_BITS; ++i) wp[i] = trial[i];
+      for (int i = 0; i < warp_bits; ++i) wp[i] = trial[i];
       ++e;
     }
     if (e == s) {                       // no room for warp-owned positions: plain block-synchronised step
@@ -864,7 +868,9 @@ void assign_runs(QsPass& P) {
       ++s;
       continue;
     }
-    if (e == s + 1 && !lanes_ok(s, (1u << wp[0]) | (1u << wp[1]) | (1u << wp[2])) && lanes_ok(s, 0)) {
+    uint32_t wp_mask = 0;
+    for (int i = 0; i < warp_bits; ++i) wp_mask |= 1u << wp[i];
+    if (e == s + 1 && !lanes_ok(s, wp_mask) && lanes_ok(s, 0)) {
       // a run of one step gains nothing from warp-owned positions
       order_free_positions(P.steps[s], T, nullptr, 0);
       P.steps[s].block_sync = 1;
@@ -872,7 +878,7 @@ void assign_runs(QsPass& P) {
       continue;
     }
     for (int i = s; i < e; ++i) {
-      order_free_positions(P.steps[i], T, wp, QS_WARP_BITS);
+      order_free_positions(P.steps[i], T, wp, warp_bits);
       P.steps[i].block_sync = (i == e - 1) ? 1 : 0;
     }
     s = e;
@@ -883,6 +889,7 @@ void assign_runs(QsPass& P) {
 // assign_runs): where the amplitudes of a work item and the per-thread iterations sit.
 void finish_tables(QsPass& P) {
   const int T = (int)P.T;
+  const int thr_log2 = (int)P.cta_log2;
   for (uint32_t s = 0; s < P.nsteps; ++s) {
     QsStep& st = P.steps[s];
     const int r = st.r;
@@ -893,10 +900,10 @@ void finish_tables(QsPass& P) {
       st.sdepb[m] = qs_swz(d) << 4;
     }
     const int nfree = T - r;
-    const int lo_bits = std::min(nfree, QS_THREADS_LOG2);
+    const int lo_bits = std::min(nfree, thr_log2);
     for (int i = 0; i < QS_MAX_WORK; ++i) {
       const uint32_t jhi =
-          i < (1 << (nfree - lo_bits)) ? qs_scatter8((uint32_t)i, st.fpos + QS_THREADS_LOG2, nfree - lo_bits) : 0u;
+          i < (1 << (nfree - lo_bits)) ? qs_scatter8((uint32_t)i, st.fpos + thr_log2, nfree - lo_bits) : 0u;
       st.hi[i] = jhi | (qs_swz(jhi) << 16);
     }
   }
@@ -994,6 +1001,19 @@ int build_plan(int n, const std::vector<Op>& ops, const qsim_plan_options_t& opt
     if (taken.empty())
       return fail(QSIM_ERR_UNSUPPORTED, "planner made no progress (tile too small for the next gate)");
     for (size_t idx : taken) done[idx] = 1;
+    {
+      // Threads per CTA.  A pass with 16-amplitude steps needs ~120 registers per thread: 256-thread
+      // CTAs then fit two to an SM, 128-thread CTAs three (the 64 KiB tiles allow no more), and three
+      // independent load / compute / store phases on an SM beat two although the warps are fewer
+      // (measured).  Passes with 8-amplitude steps fit three 256-thread CTAs and
+      // keep them.  (Every thread must find its work items in st.hi[]: 2^(T-1) / threads <= QS_MAX_WORK.)
+      int maxr = 0;
+      for (uint32_t st = 0; st < P.nsteps; ++st) maxr = std::max(maxr, (int)P.steps[st].r);
+      int cta = opt.cta_log2;
+      if (cta == 0) cta = maxr >= 4 ? QS_THREADS_LOG2_MIN : QS_THREADS_LOG2;
+      if ((int)P.T - 1 - cta > 4) cta = QS_THREADS_LOG2;
+      P.cta_log2 = (uint8_t)cta;
+    }
     assign_runs(P);
     finish_tables(P);
     for (uint32_t s = 0; s < P.nsteps; ++s) {

@@ -27,7 +27,8 @@ if os.environ.get("QSIM_LIB"):          # development: try an experimental build
 
 # Planner knobs (0 = library default); bench.py sweeps these.
 PLAN_OPTIONS = {"tile_bits": 0, "low_bits": 0, "max_group": 0, "max_dense_ops": 0, "lookahead": 0,
-                "merge_1q": 0, "defer_tail": 0, "max_layers": 0, "apply_tail_mask": 0}
+                "merge_1q": 0, "defer_tail": 0, "max_layers": 0, "cta_log2": 0, "reserved0": 0,
+                "apply_tail_mask": 0}
 
 
 def _as_c128(arr) -> np.ndarray:

@@ -286,7 +286,8 @@ def check_random_vs_oracle(backend, trials, n_range, tile_range, seed):
         n = int(rng.integers(n_range[0], n_range[1] + 1))
         opts = dict(tile_bits=int(rng.integers(tile_range[0], tile_range[1] + 1)),
                     low_bits=int(rng.integers(0, 5)), max_group=int(rng.integers(1, 5)),
-                    max_dense_ops=int(rng.integers(1, 24)), merge_1q=int(rng.integers(1, 3)))
+                    max_dense_ops=int(rng.integers(1, 24)), merge_1q=int(rng.integers(1, 3)),
+                    cta_log2=int(rng.choice([0, 7, 8])))
         psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
         psi /= np.linalg.norm(psi)
         circ = random_circuit(n, int(rng.integers(1, 80)), rng)
