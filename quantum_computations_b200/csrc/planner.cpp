@@ -13,6 +13,7 @@
 #include "tile_exec.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace qs {
@@ -153,6 +154,7 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector
   std::vector<Op> out;
   out.reserve(in.size());
   std::vector<BitTrack> tr(n);
+  static const bool quarter_turns = [] { const char* e = getenv("QSIM_NO_QUARTER_TURNS"); return !(e && atoi(e) != 0); }();
 
   auto emit_pending = [&](int b) {
     BitTrack& t = tr[b];
@@ -180,11 +182,24 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector
     double c, s;
     if (!o.diag && !is_antidiagonal(o.mat) && factor_rotation(o.mat, l0, l1, c, s, r1)) {
       o.rot = true;
-      o.c = c; o.s = s; o.r0 = cplx(1.0, 0.0); o.r1 = r1;
-      o.mat = {cplx(c, 0.0), -s * r1, cplx(s, 0.0), c * r1};
+      o.r0 = cplx(1.0, 0.0); o.r1 = r1;
       t.has_pending = true;
-      t.pending = {l0, cplx(0.0, 0.0), cplx(0.0, 0.0), l1};
-      t.pending_diag = true;
+      if (s <= c || !quarter_turns) {
+        o.c = c; o.s = s;
+        o.mat = {cplx(c, 0.0), -s * r1, cplx(s, 0.0), c * r1};
+        t.pending = {l0, cplx(0.0, 0.0), cplx(0.0, 0.0), l1};
+        t.pending_diag = true;
+      } else {
+        // More than 45 degrees: split off a quarter turn,
+        //   [[c, -s], [s, c]] = [[0, -1], [1, 0]] . [[s, c], [-c, s]],
+        // which stays behind with the left phases as an ANTIDIAGONAL pending product (it slides
+        // through CZ/Z like any bit flip, see below).  What is emitted turns by at most 45
+        // degrees, the two-shear form of the kernel (plan.h).
+        o.c = s; o.s = -c;
+        o.mat = {cplx(s, 0.0), c * r1, cplx(-c, 0.0), s * r1};
+        t.pending = {cplx(0.0, 0.0), -l0, l1, cplx(0.0, 0.0)};
+        t.pending_diag = false;
+      }
     }
     out.push_back(o);
     t.last_op = (int)out.size() - 1;
@@ -323,10 +338,10 @@ struct OneQ {
   bool full = false;                            // needs a QS_LAYER_GENERAL layer
 };
 
-// [[c, -s], [s, c]] . diag(r0, r1) with c, s >= 0, c^2 + s^2 = 1 (plan.h)
+// [[c, -s], [s, c]] . diag(r0, r1) with c >= 0, c^2 + s^2 = 1 (plan.h); s < 0 only with c >= |s|
 OneQ rotation_form(double c, double s, cplx r0, cplx r1) {
   OneQ q;
-  if (c >= s) {
+  if (c >= std::abs(s)) {
     const double t = s / c, d = 1.0 + t * t;
     q.form = QS_FORM_TAN; q.c0 = t / d; q.c1 = t;
     q.ph0 = c * r0; q.ph1 = (c * d) * r1;
