@@ -293,7 +293,7 @@ def secondary_grover() -> dict:
             "max_rel_err_vs_reference_vectors": worst}
 
 
-def secondary_dm(n: int = 12, depth: int = 100) -> dict:
+def secondary_dm(n: int = 12, depth: int = 100, plan_opts: dict | None = None) -> dict:
     """C3: n-qubit density matrix (2n-bit vec), layered Clifford+T circuit, a GKP channel after
     every gate; parity of the same generator at n = 6 against the CPU oracle."""
     import torch
@@ -311,7 +311,7 @@ def secondary_dm(n: int = 12, depth: int = 100) -> dict:
     for g in circ:
         ops.extend(g.lowered(n, True))
     t0 = time.perf_counter()
-    plan = engine.Plan(be, 2 * n, ops)
+    plan = engine.Plan(be, 2 * n, ops, plan_opts or {})
     plan_s = time.perf_counter() - t0
 
     def fresh():

@@ -71,7 +71,8 @@
 enum QsLayerKind : uint8_t {
   QS_LAYER_ROT     = 0,   // sign, phase table, per factor none / TAN / COT
   QS_LAYER_GENERAL = 1,   // sign, phase table, per factor none / any complex 2x2 (8 doubles)
-  QS_LAYER_DENSE   = 2    // sign, then one dense 2^r x 2^r complex matrix (only layer of its step)
+  QS_LAYER_DENSE   = 2    // sign, then one dense 2^r x 2^r complex matrix, or two 4x4 blocks on factors
+                          // (0,1) and (2,3) of a 4-bit step (QS_LH_PAIR); only gate layer of its step
 };
 
 enum QsFactorForm : uint8_t {
@@ -91,6 +92,7 @@ enum QsFactorForm : uint8_t {
 #define QS_LH_FINAL    (1u << 2)
 #define QS_LH_GENERAL  (1u << 3)
 #define QS_LH_DENSE    (1u << 4)
+#define QS_LH_PAIR     (1u << 5)   // dense layer of a 4-bit step holding TWO 4x4 blocks: factors (0,1) and (2,3)
 #define QS_LH_TAN(f)    (1u << (8 + (f)))
 #define QS_LH_SHEAR3(f) (1u << (12 + (f)))
 #define QS_LH_FULL(f)   (1u << (16 + (f)))
@@ -110,7 +112,8 @@ struct alignas(16) QsLayer {
   uint16_t pair_off;             // first (local position, outer global bit) pair in QsPass::pairs
   uint16_t n_lo;
   uint16_t zconst;               // local positions carrying a Z
-  uint16_t pad1;
+  uint16_t cross;                // paired dense layer (and a final layer behind one): amplitudes m whose sign
+                                 // flips because of pairs BETWEEN the two blocks (bit m), which no 4x4 can absorb
   // in-tile partners (local positions outside the group) of group factor f live in ngp; sign
   // pairs inside the group depend on m only and are folded into the phase table (or the
   // dense matrix) by the planner

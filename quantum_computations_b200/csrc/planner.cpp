@@ -386,6 +386,7 @@ struct Walker {
     uint64_t blocked_full = 0, blocked_diag = 0;
     int dense_taken = 0, sign_taken = 0, visited = 0;
     const int max_layers = std::min(opt.max_layers, kMaxStepLayers);
+    static const bool pair_dense = [] { const char* e = getenv("QSIM_NO_DENSE_PAIRS"); return !(e && atoi(e) != 0); }();
 
     int lpos[64];
     {
@@ -578,7 +579,36 @@ struct Walker {
         const int dim = 1 << op.k;
         int nlo = 0, cnt = 0;
         for (int b : op.bits) { int lo1 = 0; cnt += pending_count(b, &lo1); nlo += lo1; }
-        if (nsteps >= QS_MAX_STEPS || nlayers >= layer_cap || ncoef + 2 * dim * dim > coef_cap ||
+        // A 4x4 block may share the round trip of an earlier 4x4 block on two other bits (paired dense
+        // layer, plan.h): the step must come after everything this op depends on, i.e. after the last
+        // matrix on its bits and on the partners of its pending pairs.
+        int join = -1;
+        if (op.k == 2 && opt.max_group >= 4 && pair_dense) {
+          const int e = std::max(earliest_pos(op.bits[0]), earliest_pos(op.bits[1]));
+          for (int sidx = (e + 63) >> 6; sidx < nsteps; ++sidx) {
+            const WStep& st = steps[sidx];
+            if (!st.dense || st.r != 2 || st.nlayers != 1) continue;
+            if (st.bits[0] == op.bits[0] || st.bits[0] == op.bits[1] || st.bits[1] == op.bits[0] ||
+                st.bits[1] == op.bits[1])
+              continue;
+            const WLayer& L = layers[st.layers[0]];
+            if (L.npairs + cnt > kMaxLayerPairs || L.nlo + nlo > kMaxLo) continue;
+            join = sidx;
+            break;
+          }
+        }
+        if (join >= 0 && ncoef + 2 * dim * dim <= coef_cap && total_lo + nlo + npend <= QS_MAX_PAIRS) {
+          WStep& st = steps[join];
+          st.bits[2] = op.bits[0];
+          st.bits[3] = op.bits[1];
+          st.r = 4;
+          const int li = st.layers[0];
+          layers[li].op_idx[1] = (int)i;
+          ncoef += 2 * dim * dim;
+          const int pos = join * 64;
+          for (int f = 0; f < op.k; ++f) attach(op.bits[f], li, pos);
+          for (int b : op.bits) last_dense[b] = pos;
+        } else if (nsteps >= QS_MAX_STEPS || nlayers >= layer_cap || ncoef + 2 * dim * dim > coef_cap ||
             cnt > kMaxLayerPairs || nlo > kMaxLo || total_lo + nlo + npend > QS_MAX_PAIRS) {
           take = false;
         } else {
@@ -633,6 +663,7 @@ struct Walker {
     }
     P.nsteps = (uint32_t)nsteps;
     int ncoef = 0, npairs = 0, nl = 0;
+    bool pair_of[QS_MAX_LAYERS + 1] = {};          // layer holds two 4x4 blocks
     for (int s = 0; s < nsteps; ++s) {
       WStep& ws = steps[s];
       QsStep& st = P.steps[s];
@@ -655,7 +686,18 @@ struct Walker {
         L.step = (uint8_t)s;
         const int r = ws.r, na = 1 << r;
         // coefficients
-        if (wl.kind == QS_LAYER_DENSE) {
+        const bool paired = wl.kind == QS_LAYER_DENSE && wl.op_idx[1] >= 0;
+        pair_of[nl - 1] = paired;
+        if (paired) {
+          L.coef_off = (uint16_t)ncoef;
+          for (int blk = 0; blk < 2; ++blk) {
+            const Op& op = ops[wl.op_idx[blk]];
+            for (int e = 0; e < 16; ++e) {
+              P.coef[ncoef++] = op.mat[e].real();
+              P.coef[ncoef++] = op.mat[e].imag();
+            }
+          }
+        } else if (wl.kind == QS_LAYER_DENSE) {
           const Op& op = ops[wl.op_idx[0]];
           L.coef_off = (uint16_t)ncoef;
           for (int e = 0; e < na * na; ++e) {
@@ -737,7 +779,35 @@ struct Walker {
               if (coupled[f][f2] && ((m >> (r - 1 - f)) & 1) && ((m >> (r - 1 - f2)) & 1)) q ^= 1u;
           qg |= q << m;
         }
-        if (wl.kind == QS_LAYER_DENSE) {
+        const bool behind_pair = is_fin && ws.nlayers > 0 && layers[ws.layers[ws.nlayers - 1]].kind == QS_LAYER_DENSE &&
+                                 layers[ws.layers[ws.nlayers - 1]].op_idx[1] >= 0;
+        if (paired || behind_pair) {
+          // Pairs inside block A (factors 0,1) or inside block B (factors 2,3) go into the columns of
+          // that 4x4 (rows, for the final layer behind it); pairs BETWEEN the blocks depend on both
+          // block indices and travel as the 16-bit sign pattern `cross`.
+          QsLayer& D = paired ? L : P.layers[nl - 2];
+          const bool inA = coupled[0][1], inB = coupled[2][3];
+          for (int blk = 0; blk < 2; ++blk) {
+            if (!(blk == 0 ? inA : inB)) continue;
+            double* m4 = P.coef + D.coef_off + 32 * blk;
+            for (int row = 0; row < 4; ++row)
+              for (int c = 0; c < 4; ++c) {
+                const int idx = paired ? c : row;              // column (before) / row (after) index 3 = both bits set
+                if (idx != 3) continue;
+                m4[2 * (row * 4 + c)] *= -1.0;
+                m4[2 * (row * 4 + c) + 1] *= -1.0;
+              }
+          }
+          uint32_t cross = 0;
+          for (int m = 0; m < na; ++m) {
+            uint32_t q = 0;
+            for (int f = 0; f < 2; ++f)
+              for (int f2 = 2; f2 < 4; ++f2)
+                if (coupled[f][f2] && ((m >> (r - 1 - f)) & 1) && ((m >> (r - 1 - f2)) & 1)) q ^= 1u;
+            cross |= q << m;
+          }
+          L.cross = (uint16_t)cross;
+        } else if (wl.kind == QS_LAYER_DENSE) {
           for (int row = 0; row < na; ++row)
             for (int c = 0; c < na; ++c)
               if (qg >> c & 1) {
@@ -773,6 +843,7 @@ struct Walker {
       if (L.flags & QS_LF_FINAL) h |= QS_LH_FINAL;
       if (L.kind == QS_LAYER_GENERAL) h |= QS_LH_GENERAL;
       if (L.kind == QS_LAYER_DENSE) h |= QS_LH_DENSE;
+      if (L.kind == QS_LAYER_DENSE && P.steps[L.step].r == 4 && pair_of[l]) h |= QS_LH_PAIR;
       for (int f = 0; f < QS_MAX_R; ++f) {
         if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_TAN) h |= QS_LH_TAN(f);
         if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_SHEAR3) h |= QS_LH_SHEAR3(f);

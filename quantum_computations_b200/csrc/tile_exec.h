@@ -288,6 +288,55 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
 #pragma unroll
         for (int m = 0; m < NA; ++m) qs_flip(a[m], S[m]);
       }
+      if (DENSE && R == 4 && (head & QS_LH_PAIR)) {
+        // two dense 4x4 blocks in one round trip: A on factors (0,1) = bits 3,2 of m, then B on
+        // factors (2,3) = bits 1,0 (density-matrix channels: one block per (q, q+N) pair)
+        const double* const matA = P.coef + (H.offs & 0xffffu);
+        const double* const matB = matA + 32;
+        uint32_t S2[NA];
+#pragma unroll
+        for (int m = 0; m < NA; ++m) S2[m] = 0u;
+        uint32_t cross2 = 0u;
+        if (l + 1 < l_end) {                          // the pass's final sign layer
+          const QsLayerHot H2 = qs_layer_hot(P, l + 1);
+          qs_layer_sign<R>(P, H2, zm[l + 1], j0, jlo, i, fin_g, fin_qlo, S2);
+          cross2 = P.layers[l + 1].cross;
+        }
+        const uint32_t cross1 = P.layers[l].cross;
+#pragma unroll
+        for (int m = 0; m < NA; ++m) qs_flip(a[m], (cross1 >> m) << 31);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const double* const mat = half ? matB : matA;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            // the four amplitudes of this block application: index e -> m
+            qs_c128 in[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) in[e] = a[half ? (g * 4 + e) : (e * 4 + g)];
+#pragma unroll
+            for (int row = 0; row < 4; ++row) {
+              double re = 0.0, im = 0.0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const double mr = mat[2 * (row * 4 + c)], mi = mat[2 * (row * 4 + c) + 1];
+                re += mr * in[c].x - mi * in[c].y;
+                im += mr * in[c].y + mi * in[c].x;
+              }
+              qs_c128& o = a[half ? (g * 4 + row) : (row * 4 + g)];
+              o.x = re; o.y = im;
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < NA; ++m) qs_flip(a[m], S2[m] ^ ((cross2 >> m) << 31));
+        if (active) {
+#pragma unroll
+          for (int m = 0; m < NA; ++m) *reinterpret_cast<qs_c128*>(t0 + (s0b ^ st.sdepb[m])) = a[m];
+        }
+        stored = true;
+        break;
+      }
       if (DENSE && (head & QS_LH_DENSE)) {
         // dense 2^R x 2^R matrix: inputs are all in registers, so rows can be
         // written back one at a time (4x4: unrolled, the coefficients become uniform operands;
