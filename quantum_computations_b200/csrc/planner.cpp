@@ -386,6 +386,7 @@ struct Walker {
     uint64_t blocked_full = 0, blocked_diag = 0;
     int dense_taken = 0, sign_taken = 0, visited = 0;
     const int max_layers = std::min(opt.max_layers, kMaxStepLayers);
+    static const bool pad_steps = [] { const char* e = getenv("QSIM_NO_STEP_PADDING"); return !(e && atoi(e) != 0); }();
     static const bool pair_dense = [] { const char* e = getenv("QSIM_NO_DENSE_PAIRS"); return !(e && atoi(e) != 0); }();
 
     int lpos[64];
@@ -637,6 +638,25 @@ struct Walker {
       if ((blocked_full & all) == all) break;
     }
 
+    if (pass && pad_steps) {
+      // A step with fewer group bits than the widest one runs a smaller instantiation of the step
+      // body, and ptxas keeps only the widest one's layer loop on the uniform datapath (DESIGN.md
+      // section 5).  An idle group bit costs nothing (no rotation, phase 1, one more popcount), so
+      // narrow rotation steps are widened with tile bits they do not use, highest positions first
+      // (positions below 6 are the ones the conflict-free thread maps need).
+      int widest = 0;
+      for (int sidx = 0; sidx < nsteps; ++sidx) widest = std::max(widest, steps[sidx].r);
+      for (int sidx = 0; sidx < nsteps; ++sidx) {
+        WStep& st = steps[sidx];
+        if (st.dense) continue;
+        for (int b = n - 1; b >= 0 && st.r < widest; --b) {
+          if (!(S >> b & 1) || lpos[b] < 6) continue;
+          bool member = false;
+          for (int f = 0; f < st.r; ++f) member |= st.bits[f] == b;
+          if (!member) st.bits[st.r++] = b;
+        }
+      }
+    }
     if (pass) finalize(*pass, S, lpos, steps, nsteps, layers, pend, npend);
     return (long)dense_taken * 4096 + std::min(sign_taken, 4095);
   }
