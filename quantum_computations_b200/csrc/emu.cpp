@@ -89,8 +89,10 @@ void emu_pass(const QsPass& P, qs_c128* state, int n) {
     for (int s = 0; s < nsteps; ++s) {
       for (uint32_t tid = 0; tid < nthreads; ++tid) {
         // same variant selection as launch_pass() in kernels.cu
-        if (dense) qs_phase_step_any<4, true>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
-        else qs_phase_step_any<4, false>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        // the three dense modes of launch_pass() in kernels.cu run the same step bodies
+        if (dense && (t & 1)) qs_phase_step_any<4, 2>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        else if (dense) qs_phase_step_any<4, 1>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
+        else qs_phase_step_any<4, 0>(P, s, tile.data(), tid, thr_log2, zm.data(), fin_g, fin_qlo[tid], tab[s]);
       }
       if (t == 0) check_warp_ownership(P, s, tab[s]);
     }

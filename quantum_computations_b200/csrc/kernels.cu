@@ -39,7 +39,7 @@ struct DevCtx {
   double* d_out = nullptr;        // [2]
   double* h_out = nullptr;        // pinned [2]
   std::mutex occ_lock;
-  int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // resident CTAs/SM of the k_tile_pass variants at the last smem size
+  int occ[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // resident CTAs/SM of the k_tile_pass variants at the last smem size
   int occ_smem = -1;
 };
 
@@ -151,7 +151,7 @@ __device__ __forceinline__ void tma_box_coords(const QsPass& P, const QsTmaGeom&
 // the steps of the other two.
 // TL2 = log2 threads per CTA (QsPass::cta_log2): 128-thread CTAs run three (smem-limited) or four
 // to an SM, 256-thread CTAs two (16 amplitudes per thread) or three (8 per thread).
-template <int MAXR, bool DENSE, int TL2>
+template <int MAXR, int DENSE, int TL2>
 __global__ void __launch_bounds__(1 << TL2, (TL2 == 7 ? (MAXR <= 3 ? 6 : 4) : (MAXR <= 3 ? 3 : 2)))
 k_tile_pass(qs_c128* state, const __grid_constant__ QsPass P, const __grid_constant__ CUtensorMap tmap,
             const __grid_constant__ QsTmaGeom G, uint64_t ntiles) {
@@ -322,21 +322,30 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   int maxr = 1;
   bool dense = false;
   for (uint32_t s = 0; s < P.nsteps; ++s) maxr = P.steps[s].r > maxr ? P.steps[s].r : maxr;
-  for (uint32_t l = 0; l < P.nlayers; ++l) dense |= P.layers[l].kind == QS_LAYER_DENSE;
-  static const TileKernel variants[8] = {
-      k_tile_pass<3, false, 8>, k_tile_pass<3, true, 8>, k_tile_pass<4, false, 8>, k_tile_pass<4, true, 8>,
-      k_tile_pass<3, false, 7>, k_tile_pass<3, true, 7>, k_tile_pass<4, false, 7>, k_tile_pass<4, true, 7>};
+  int dense_steps = 0;
+  for (uint32_t s = 0; s < P.nsteps; ++s) dense_steps += P.layers[P.steps[s].layer0].kind == QS_LAYER_DENSE ? 1 : 0;
+  dense = dense_steps > 0;
+  // dense mode of the kernel (tile_exec.h, qs_phase_step_any): mostly dense steps -> all inline
+  int dense_mode = dense_steps == 0 ? 0 : (2 * dense_steps > (int)P.nsteps ? 2 : 1);
+  static const int force_dense = [] { const char* e = getenv("QSIM_FORCE_DENSE_VARIANT"); return e ? atoi(e) : 0; }();
+  if (force_dense == 1 || force_dense == 2) dense_mode = std::max(dense_mode, force_dense);   // development knob
+  // [cta size][MAXR 3 / 4][dense mode 0 / 1 / 2]
+  static const TileKernel variants[12] = {
+      k_tile_pass<3, 0, 8>, k_tile_pass<3, 1, 8>, k_tile_pass<3, 2, 8>,
+      k_tile_pass<4, 0, 8>, k_tile_pass<4, 1, 8>, k_tile_pass<4, 2, 8>,
+      k_tile_pass<3, 0, 7>, k_tile_pass<3, 1, 7>, k_tile_pass<3, 2, 7>,
+      k_tile_pass<4, 0, 7>, k_tile_pass<4, 1, 7>, k_tile_pass<4, 2, 7>};
   if (P.cta_log2 != QS_THREADS_LOG2_MIN && P.cta_log2 != QS_THREADS_LOG2)
     return qs::fail(QSIM_ERR_ARG, "pass built for an unsupported CTA size");
   const int threads = 1 << P.cta_log2;
-  const int vi = (P.cta_log2 == QS_THREADS_LOG2 ? 0 : 4) + (maxr <= 3 ? 0 : 2) + (dense ? 1 : 0);
+  const int vi = (P.cta_log2 == QS_THREADS_LOG2 ? 0 : 6) + (maxr <= 3 ? 0 : 3) + dense_mode;
   int occ;
   {
     std::lock_guard<std::mutex> guard(ctx->occ_lock);
     if (ctx->occ_smem != smem) {
-      for (int v = 0; v < 8; ++v) {
+      for (int v = 0; v < 12; ++v) {
         QS_CUDA(cudaFuncSetAttribute(variants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], v < 4 ? 256 : 128, smem));
+        QS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[v], variants[v], v < 6 ? 256 : 128, smem));
       }
       ctx->occ_smem = smem;
     }

@@ -434,16 +434,55 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
   }
 }
 
-// MAXR bounds the instantiated group sizes (and with them the register budget
-// of the calling kernel); DENSE says whether dense (k >= 2) layers may occur.
-template <int MAXR, bool DENSE>
+// A dense step (its first layer is a QS_LAYER_DENSE layer) runs OUT OF LINE on the device: with
+// the dense bodies inlined next to the rotation bodies ptxas takes the rotation steps' layer loop
+// off the uniform datapath (a kernel that can take dense layers ran 24 % slower on a circuit
+// without any).
+#if defined(__CUDACC__)
+#define QS_NOINLINE_DEVICE __noinline__
+#else
+#define QS_NOINLINE_DEVICE
+#endif
+template <int MAXR>
+QS_NOINLINE_DEVICE
+#if defined(__CUDACC__)
+__host__ __device__
+#else
+inline
+#endif
+void qs_dense_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2, const uint32_t* zm,
+                       uint32_t fin_g, uint32_t fin_qlo, const QsStepTab& tab) {
+  const int r = P.steps[s].r;
+  if (r == 2) qs_phase_step<2, true, false>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (r == 3) qs_phase_step<3, true, false>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (MAXR >= 4 && r == 4)
+    qs_phase_step<(MAXR >= 4 ? 4 : 2), true, false>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+}
+
+// MAXR bounds the instantiated group sizes (and with them the register budget of the calling
+// kernel).  DENSE: 0 = the pass has no dense layer; 1 = a few dense steps among rotation steps:
+// the dense ones run out of line, the rotation steps keep the uniform datapath; 2 = mostly dense
+// steps (density-matrix channels): everything inline, the dense bodies get the uniform operands.
+template <int MAXR, int DENSE>
 QS_HD void qs_phase_step_any(const QsPass& P, int s, qs_c128* tile, uint32_t tid, uint32_t nthr_log2,
                              const uint32_t* zm, uint32_t fin_g, uint32_t fin_qlo, const QsStepTab& tab) {
   constexpr bool ZASM = MAXR >= 4;
   const int r = P.steps[s].r;
+  if (DENSE == 2) {
+    if (r == 1) qs_phase_step<1, false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    else if (r == 2) qs_phase_step<2, true, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    else if (r == 3) qs_phase_step<3, true, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    else if (MAXR >= 4 && r == 4)
+      qs_phase_step<(MAXR >= 4 ? 4 : 1), true, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    return;
+  }
+  if (DENSE == 1 && P.layers[P.steps[s].layer0].kind == QS_LAYER_DENSE) {
+    qs_dense_step_any<MAXR>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    return;
+  }
   if (r == 1) qs_phase_step<1, false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
-  else if (r == 2) qs_phase_step<2, DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
-  else if (r == 3) qs_phase_step<3, DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (r == 2) qs_phase_step<2, false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+  else if (r == 3) qs_phase_step<3, false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
   else if (MAXR >= 4 && r == 4)
-    qs_phase_step<(MAXR >= 4 ? 4 : 1), DENSE, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
+    qs_phase_step<(MAXR >= 4 ? 4 : 1), false, ZASM>(P, s, tile, tid, nthr_log2, zm, fin_g, fin_qlo, tab);
 }

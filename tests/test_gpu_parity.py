@@ -126,11 +126,13 @@ def test_dm_layers(cuda_backend):
     pc.check_dm_layers_vs_oracle(cuda_backend, n=8, depth=2, seed=12)
 
 
-def test_sv_22q_vs_oracle(cuda_backend):
-    """Config C4's generator at a size the strided oracle still finishes in seconds."""
+@pytest.mark.parametrize("cta_log2", [0, 7, 8])
+def test_sv_22q_vs_oracle(cuda_backend, cta_log2):
+    """Config C4's generator at a size the strided oracle still finishes in seconds, on both CTA
+    sizes of the tile pass (1024 tiles: every CTA loops over several)."""
     n, depth = 22, 3
     circ = workloads.sv_random_circuit(n, depth, 30)
-    got = Simulator(circ, backend=cuda_backend).run([State.ZERO] * n)
+    got = Simulator(circ, backend=cuda_backend, plan_options={"cta_log2": cta_log2}).run([State.ZERO] * n)
     psi0 = np.zeros(2 ** n, dtype=np.complex128)
     psi0[0] = 1.0
     ref, _ = strided.run(as_oracle_ops(circ), psi0)
