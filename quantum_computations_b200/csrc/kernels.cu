@@ -453,6 +453,8 @@ struct ExchGeom {
   int mine[8];                // this rank's value of the rank bit traded against pos[i]
   qs_c128* peer[256];         // peer[d]: partner shard for the bit pattern d (over pos[] order); [0] unused
   unsigned char higher[256];  // higher[d] = 1 if this rank's number is above the partner's
+  int chunk_log2;             // > 0: work is dealt to the partners in chunks of 2^chunk_log2 pairs (round robin),
+                              // so that all 2^k - 1 partners are being talked to at any time; 0: partner after partner
 };
 constexpr int kExchSplitBit = 5;
 
@@ -474,8 +476,16 @@ k_exchange_p2p(qs_c128* __restrict__ shard, const __grid_constant__ ExchGeom G) 
       const uint64_t w = w0 + (uint64_t)u * blockDim.x;
       mine[u] = nullptr;
       if (w >= total) continue;
-      const int d = 1 + (int)(w / half);
-      const uint64_t q = w % half;
+      int d;
+      uint64_t q;
+      if (G.chunk_log2 > 0) {
+        const uint64_t chunk = w >> G.chunk_log2, nd = (1ull << k) - 1ull;
+        d = 1 + (int)(chunk % nd);
+        q = ((chunk / nd) << G.chunk_log2) | (w & ((1ull << G.chunk_log2) - 1ull));
+      } else {
+        d = 1 + (int)(w / half);
+        q = w % half;
+      }
       // r: index inside the block; bit kExchSplitBit says which of the two ranks moves it
       const uint64_t low = q & ((1ull << kExchSplitBit) - 1ull);
       const uint64_t r = ((q >> kExchSplitBit) << (kExchSplitBit + 1)) | ((uint64_t)G.higher[d] << kExchSplitBit) | low;
@@ -968,6 +978,8 @@ int qsim_exchange_p2p(void* shard, void* const* peer_shards, int n_local, int nb
   // development knobs (defaults measured on 2 and 8 B200s): pairs per thread and trip, CTAs per SM
   static const int batch = [] { const char* e = getenv("QSIM_EXCH_BATCH"); return e ? atoi(e) : 4; }();
   static const int per_sm = [] { const char* e = getenv("QSIM_EXCH_CTAS"); return e ? atoi(e) : 8; }();
+  static const int chunk_log2 = [] { const char* e = getenv("QSIM_EXCH_CHUNK_LOG2"); return e ? atoi(e) : 0; }();
+  G.chunk_log2 = (chunk_log2 > 0 && chunk_log2 <= n_local - nbits - 1 && nbits > 1) ? chunk_log2 : 0;
   const int U = batch >= 8 ? 8 : batch >= 4 ? 4 : batch >= 2 ? 2 : 1;
   uint64_t blocks = (total + 256ull * U - 1) / (256ull * U);
   const uint64_t cap = (uint64_t)bound.ctx->sms * (uint64_t)(per_sm > 0 ? per_sm : 8);
