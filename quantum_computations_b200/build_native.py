@@ -49,6 +49,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
            "-o", CUDA_LIB] + srcs
+    if os.environ.get("QSIM_DEV_KNOBS"):          # development build: A/B switches read the environment
+        cmd.insert(1, "-DQSIM_DEV_KNOBS")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

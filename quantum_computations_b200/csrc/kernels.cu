@@ -256,7 +256,7 @@ PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
 void make_tma_geom(const QsPass& P, qs_c128* state, int n, QsTmaGeom* G, CUtensorMap* map) {
   memset(G, 0, sizeof(*G));
   memset(map, 0, sizeof(*map));
-  static const bool off = [] { const char* e = getenv("QSIM_NO_TMA"); return e && atoi(e) != 0; }();
+  static const bool off = qs::dev_knob("QSIM_NO_TMA", 0) != 0;
   PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
   const int T = (int)P.T;
   if (off || !enc || n < 12 || n > 40 || T < 6) return;
@@ -327,7 +327,7 @@ int launch_pass(DevCtx* ctx, const QsPass& P, qs_c128* state, int n, cudaStream_
   dense = dense_steps > 0;
   // dense mode of the kernel (tile_exec.h, qs_phase_step_any): mostly dense steps -> all inline
   int dense_mode = dense_steps == 0 ? 0 : (2 * dense_steps > (int)P.nsteps ? 2 : 1);
-  static const int force_dense = [] { const char* e = getenv("QSIM_FORCE_DENSE_VARIANT"); return e ? atoi(e) : 0; }();
+  static const int force_dense = qs::dev_knob("QSIM_FORCE_DENSE_VARIANT", 0);
   if (force_dense == 1 || force_dense == 2) dense_mode = std::max(dense_mode, force_dense);   // development knob
   // [cta size][MAXR 3 / 4][dense mode 0 / 1 / 2]
   static const TileKernel variants[12] = {
@@ -976,9 +976,9 @@ int qsim_exchange_p2p(void* shard, void* const* peer_shards, int n_local, int nb
   if (rc != QSIM_OK) return rc;
   const uint64_t total = (1ull << (n_local - nbits - 1)) * ((1ull << nbits) - 1ull);
   // development knobs (defaults measured on 2 and 8 B200s): pairs per thread and trip, CTAs per SM
-  static const int batch = [] { const char* e = getenv("QSIM_EXCH_BATCH"); return e ? atoi(e) : 4; }();
-  static const int per_sm = [] { const char* e = getenv("QSIM_EXCH_CTAS"); return e ? atoi(e) : 8; }();
-  static const int chunk_log2 = [] { const char* e = getenv("QSIM_EXCH_CHUNK_LOG2"); return e ? atoi(e) : 0; }();
+  static const int batch = qs::dev_knob("QSIM_EXCH_BATCH", 4);
+  static const int per_sm = qs::dev_knob("QSIM_EXCH_CTAS", 8);
+  static const int chunk_log2 = qs::dev_knob("QSIM_EXCH_CHUNK_LOG2", 0);
   G.chunk_log2 = (chunk_log2 > 0 && chunk_log2 <= n_local - nbits - 1 && nbits > 1) ? chunk_log2 : 0;
   const int U = batch >= 8 ? 8 : batch >= 4 ? 4 : batch >= 2 ? 2 : 1;
   uint64_t blocks = (total + 256ull * U - 1) / (256ull * U);

@@ -154,7 +154,7 @@ std::vector<Op> merge_single_qubit(int n, const std::vector<Op>& in, std::vector
   std::vector<Op> out;
   out.reserve(in.size());
   std::vector<BitTrack> tr(n);
-  static const bool quarter_turns = [] { const char* e = getenv("QSIM_NO_QUARTER_TURNS"); return !(e && atoi(e) != 0); }();
+  static const bool quarter_turns = dev_knob("QSIM_NO_QUARTER_TURNS", 0) == 0;
 
   auto emit_pending = [&](int b) {
     BitTrack& t = tr[b];
@@ -386,8 +386,8 @@ struct Walker {
     uint64_t blocked_full = 0, blocked_diag = 0;
     int dense_taken = 0, sign_taken = 0, visited = 0;
     const int max_layers = std::min(opt.max_layers, kMaxStepLayers);
-    static const bool pad_steps = [] { const char* e = getenv("QSIM_NO_STEP_PADDING"); return !(e && atoi(e) != 0); }();
-    static const bool pair_dense = [] { const char* e = getenv("QSIM_NO_DENSE_PAIRS"); return !(e && atoi(e) != 0); }();
+    static const bool pad_steps = dev_knob("QSIM_NO_STEP_PADDING", 0) == 0;
+    static const bool pair_dense = dev_knob("QSIM_NO_DENSE_PAIRS", 0) == 0;
 
     int lpos[64];
     {

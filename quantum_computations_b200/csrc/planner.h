@@ -3,6 +3,7 @@
 #pragma once
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -60,6 +61,19 @@ struct qsim_plan {
 };
 
 namespace qs {
+
+// Development knobs (A/B switches behind the measurements in DESIGN.md section 5) read the
+// environment only in builds with -DQSIM_DEV_KNOBS; the shipped library ignores it.  Every knob
+// selects between CORRECT variants; none changes results.
+inline int dev_knob(const char* name, int fallback) {
+#if defined(QSIM_DEV_KNOBS)
+  const char* e = getenv(name);
+  return e ? atoi(e) : fallback;
+#else
+  (void)name;
+  return fallback;
+#endif
+}
 
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
