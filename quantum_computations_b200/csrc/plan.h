@@ -92,6 +92,7 @@ enum QsFactorForm : uint8_t {
 #define QS_LH_FINAL    (1u << 2)
 #define QS_LH_GENERAL  (1u << 3)
 #define QS_LH_DENSE    (1u << 4)
+#define QS_LH_SHEAR3ANY (1u << 6)  // some factor of the layer has the three-shear form (rare: quarter turns only)
 #define QS_LH_PAIR     (1u << 5)   // dense layer of a 4-bit step holding TWO 4x4 blocks: factors (0,1) and (2,3)
 #define QS_LH_TAN(f)    (1u << (8 + (f)))
 #define QS_LH_SHEAR3(f) (1u << (12 + (f)))

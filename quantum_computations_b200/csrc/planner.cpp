@@ -866,7 +866,7 @@ struct Walker {
       if (L.kind == QS_LAYER_DENSE && P.steps[L.step].r == 4 && pair_of[l]) h |= QS_LH_PAIR;
       for (int f = 0; f < QS_MAX_R; ++f) {
         if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_TAN) h |= QS_LH_TAN(f);
-        if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_SHEAR3) h |= QS_LH_SHEAR3(f);
+        if (L.kind == QS_LAYER_ROT && L.form[f] == QS_FORM_SHEAR3) h |= QS_LH_SHEAR3(f) | QS_LH_SHEAR3ANY;
         if (L.kind == QS_LAYER_GENERAL && L.form[f] == QS_FORM_FULL) h |= QS_LH_FULL(f);
       }
       L.head = h;

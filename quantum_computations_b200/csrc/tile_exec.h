@@ -381,7 +381,20 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
           a[m].y = qs_fma(ph.x, a[m].y, t2);
         }
       }
-      if (!(head & QS_LH_GENERAL)) {
+      if (!(head & (QS_LH_GENERAL | QS_LH_SHEAR3ANY))) {
+        // the common case: two-shear rotations only -- one test per factor
+        const uint32_t coef_off = H.offs & 0xffffu;
+#pragma unroll
+        for (int f = 0; f < R; ++f) {
+          const int bit = 1 << (R - 1 - f);
+          if (head & QS_LH_TAN(f)) {
+            const qs_d2 cf = qs_coef2(P, coef_off + 2 * f);
+#pragma unroll
+            for (int m = 0; m < NA; ++m)
+              if (!(m & bit)) qs_rot_tan(cf.x, cf.y, a[m], a[m | bit]);
+          }
+        }
+      } else if (!(head & QS_LH_GENERAL)) {
         const uint32_t coef_off = H.offs & 0xffffu;
 #pragma unroll
         for (int f = 0; f < R; ++f) {
