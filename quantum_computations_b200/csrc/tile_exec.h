@@ -275,6 +275,42 @@ QS_HD void qs_phase_step(const QsPass& P, int s, qs_c128* tile, uint32_t tid, ui
     for (int l = (int)st.layer0; l < l_end; ++l) {
       const QsLayerHot H = qs_layer_hot(P, l);
       const uint32_t head = H.head;
+      if (!DENSE && (head & 0xffu) == (QS_LH_SIGN | QS_LH_PHASE)) {
+        // By far the most frequent layer of a rotation step (sign block, phase table, two-shear
+        // rotations; no final part): one test up front instead of one per part -- the branch
+        // latencies of the per-part tests are a visible share of a layer at three warps per scheduler.
+        uint32_t zl;
+#if defined(__CUDA_ARCH__)
+        if (ZASM) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zl) : "r"(zm_s + 4u * (uint32_t)l));
+        else zl = zm[l];
+#else
+        zl = zm[l];
+#endif
+        uint32_t S[NA];
+        qs_layer_sign<R>(P, H, zl, j0, jlo, i, fin_g, fin_qlo, S);
+#pragma unroll
+        for (int m = 0; m < NA; ++m) qs_flip(a[m], S[m]);
+        const uint32_t ph_off = H.offs >> 16;
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+          const qs_d2 ph = qs_coef2(P, ph_off + 2 * m);
+          const double t1 = ph.y * a[m].y, t2 = ph.y * a[m].x;
+          a[m].x = qs_fma(ph.x, a[m].x, -t1);
+          a[m].y = qs_fma(ph.x, a[m].y, t2);
+        }
+        const uint32_t coef_off = H.offs & 0xffffu;
+#pragma unroll
+        for (int f = 0; f < R; ++f) {
+          const int bit = 1 << (R - 1 - f);
+          if (head & QS_LH_TAN(f)) {
+            const qs_d2 cf = qs_coef2(P, coef_off + 2 * f);
+#pragma unroll
+            for (int m = 0; m < NA; ++m)
+              if (!(m & bit)) qs_rot_tan(cf.x, cf.y, a[m], a[m | bit]);
+          }
+        }
+        continue;
+      }
       if (head & QS_LH_SIGN) {
         uint32_t zl;
 #if defined(__CUDA_ARCH__)
