@@ -49,8 +49,8 @@ METRIC_SHARDED = "gates/sec (34q c128 random circuit, depth 200, sharded over th
 
 def metric_sharded(n: int, depth: int) -> str:
     return f"gates/sec ({n}q c128 random circuit, depth {depth}, sharded over the GPUs)"
-ALT_MAX_DENSE = 8            # matrices per pass of the HBM-roof operating point (roofline_hbm_point); measured
-ALT_MAX_GROUP = 0            # curve: 6 -> 0.81, 8 -> 0.77, 12 -> 0.67, 16 -> 0.56, 28 -> 0.46
+ALT_MAX_DENSE = 10           # matrices per pass of the HBM-roof operating point (roofline_hbm_point); measured
+ALT_MAX_GROUP = 0            # curve: 8 -> 0.79, 10 -> 0.73, 12 -> 0.69, 16 -> 0.59, 20 -> 0.54
 PASS_PARAM_BYTES = 28672     # sizeof(QsPass) + tensor map + geometry: kernel parameters per tile-pass launch
 # dram__bytes_read.sum + dram__bytes_write.sum per k_tile_pass launch at n = 30, default plan options, from the
 # `ncu --set full` captures summarised in profiles/r2_ncu_full_k_tile_pass_p16.csv (17.18 GB + 17.12 GB)

@@ -610,15 +610,15 @@ class ShardedSimulator:
     def _best_plan(self, nloc, segment, options):
         """A stage is a short circuit, and its last pass is often nearly empty; planning costs
         tens of milliseconds, so try a few caps on the matrices per pass and keep the cheapest
-        plan under the measured cost model of DESIGN.md section 5 (4.1 ms per pass + 1.42 ms per
-        shared-memory round trip, per 2^30 amplitudes).  Ranks may decide differently (their
+        plan under the measured cost model of DESIGN.md section 5 (3.0 ms per pass + 0.80 ms per
+        shared-memory round trip, per 2^30 amplitudes; the matrices cost the same under every cap).  Ranks may decide differently (their
         restricted diagonals differ) -- which is fine, plans are local."""
         if options.get("max_dense_ops") or not self.dense_caps:
             return engine.Plan(self.state.backend, nloc, segment, options)
         best = None
         for cap in self.dense_caps:
             plan = engine.Plan(self.state.backend, nloc, segment, dict(options, max_dense_ops=cap))
-            key = 4.1 * plan.stats["n_passes"] + 1.42 * plan.stats["n_steps"]
+            key = 3.0 * plan.stats["n_passes"] + 0.80 * plan.stats["n_steps"]
             if best is None or key < best[0]:
                 best = (key, plan)
         return best[1]
