@@ -522,6 +522,54 @@ def check_dm_layers_vs_oracle(backend, n, depth, seed, db=10.0):
     return err
 
 
+def check_planner_features(backend):
+    """The planner features of round 2, each with the condition that makes it fire:
+    paired dense blocks (two (q, q+N) channels per round trip), rotations beyond 45 degrees
+    (quarter turn left in the Pauli frame), narrow steps widened to the widest group of a
+    pass, both CTA sizes -- all against the CPU oracle."""
+    # 1. paired dense layers: a noisy density-matrix circuit needs fewer round trips than blocks
+    n = 5
+    noise = channels.GKPNoise(10.0)
+    layers = workloads.dm_random_layers(n, 4, 3)
+    circ = noise.noisy([g for layer in layers for g in layer])
+    rho0 = np.zeros((2 ** n, 2 ** n), dtype=np.complex128)
+    rho0[0, 0] = 1.0
+    sim = Simulator(circ, backend=backend)
+    got = sim.run(rho0)
+    ref, _ = strided.run(as_oracle_ops(circ), rho0)
+    assert rel_err(got, ref) < RTOL
+    stats = sim.last_stats[0]
+    assert stats["n_steps"] < stats["n_dense"], stats            # some blocks share a step
+    # 2. rotations by every angle (RY-like real rotations and general unitaries), CZ in between
+    rng = np.random.default_rng(77)
+    n = 9
+    for cta in (0, 7, 8):
+        circ = []
+        for layer in range(6):
+            for q in range(n):
+                th = rng.uniform(-np.pi, np.pi)
+                c, s_ = np.cos(th / 2), np.sin(th / 2)
+                ph = np.exp(1j * rng.uniform(-np.pi, np.pi))
+                m = np.array([[c, -s_ * ph], [s_, c * ph]], dtype=np.complex128)
+                circ.append(gates.Gate([q], m))
+            for q in range(layer % 2, n - 1, 2):
+                circ.append(gates.CZ(q, q + 1))
+        psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        psi /= np.linalg.norm(psi)
+        got = Simulator(circ, backend=backend, plan_options={"cta_log2": cta, "tile_bits": 8}).run(psi)
+        ref, _ = strided.run(as_oracle_ops(circ), psi)
+        assert rel_err(got, ref) < RTOL, cta
+    # 3. a pass with one wide and several narrow steps (gates on 4 + 1 + 2 qubits, chained by CZ)
+    n = 10
+    circ = [gates.H(q) for q in range(4)] + [gates.CZ(0, 4), gates.H(4), gates.CZ(4, 5), gates.CZ(1, 6),
+                                             gates.H(5), gates.H(6), gates.CZ(5, 6), gates.H(0)]
+    psi = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    psi /= np.linalg.norm(psi)
+    got = Simulator(circ, backend=backend).run(psi)
+    ref, _ = strided.run(as_oracle_ops(circ), psi)
+    assert rel_err(got, ref) < RTOL
+
+
 # ---- SURVEY section 8f rows, on the device: trajectories (f1), MB layering (f2), Cliffords (f3) ---
 def _oracle_rho(circ, noise, n):
     """rho after the noisy circuit by the CPU oracle: dense operators and Kraus sums."""

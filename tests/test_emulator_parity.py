@@ -75,6 +75,10 @@ def test_dm_layers(emu_backend):
     pc.check_dm_layers_vs_oracle(emu_backend, n=6, depth=3, seed=12)
 
 
+def test_planner_features(emu_backend):
+    pc.check_planner_features(emu_backend)
+
+
 def test_trajectories_batched(emu_backend):
     pc.check_trajectories(emu_backend, shots=3000)
 

@@ -163,6 +163,11 @@ def test_circuit_then_inverse_returns_zero_state(cuda_backend, n):
     assert rest < 1e-10
 
 
+def test_planner_features(cuda_backend):
+    """Paired dense blocks, quarter-turn split, widened steps, both CTA sizes (round 2)."""
+    pc.check_planner_features(cuda_backend)
+
+
 def test_trajectories_batched(cuda_backend):
     """SURVEY 8f rank 1 on the device, against the CPU oracle."""
     pc.check_trajectories(cuda_backend, shots=20000)
