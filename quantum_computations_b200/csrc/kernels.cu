@@ -1,9 +1,10 @@
 // sm_100a kernels and the device-facing half of the C ABI (include/qsim_b200.h).
 //
-// Everything here is memory-bound complex128 work: 16-byte (128-bit) loads and
-// stores per amplitude, shared-memory staging of 2^T-amplitude tiles so several
-// gates apply per HBM pass, persistent grids sized to the SM count.  No tensor
-// cores: tcgen05 has no f64 kind and the 2x2/4x4 updates have no GEMM shape.
+// Almost everything here is memory-bound complex128 work: TMA-staged 2^T-amplitude
+// tiles in shared memory so that many gates apply per HBM pass, 16-byte (128-bit)
+// accesses per amplitude, persistent grids sized to the SM count.  Tensor cores
+// appear once: dense blocks on 5..10 qubits are FP64 MMAs (k_dense_block); tcgen05
+// has no f64 kind and the 2x2 / 4x4 updates of the tile pass have no GEMM shape.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>

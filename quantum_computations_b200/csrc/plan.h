@@ -26,6 +26,13 @@
 //                              diagonal is folded into the layer's phase table;
 //   up to 90 deg ("SHEAR3"):   [[1,-p],[0,1]] [[1,0],[q,1]] [[1,-p],[0,1]], p = tan(angle/2), q = s:
 //                              three FMAs, exact, no scale.
+// The merge pass (planner.cpp) splits a quarter turn off every rotation beyond 45 degrees and keeps
+// it in its Pauli frame, so SHEAR3 is left for explicit quarter turns (X, Y at the end of a
+// circuit); the hot loop runs TAN only, and a layer of sign block + phase table + TAN rotations --
+// four out of five layers of a random circuit -- sits behind a single test (tile_exec.h).
+//
+// Steps are widened to the widest group of their pass with idle group bits (no gate, phase 1):
+// ptxas keeps only ONE instantiation of the step body per kernel on the uniform datapath.
 //
 // Sign blocks.  CZ and Z gates multiply amplitude i by (-1)^q(i), q a quadratic
 // form over GF(2) in the index bits -- no memory traffic, any qubits.  They
@@ -69,7 +76,7 @@
 #define QS_MAX_WORK     16                                    // work items per thread and step (r >= 1)
 
 enum QsLayerKind : uint8_t {
-  QS_LAYER_ROT     = 0,   // sign, phase table, per factor none / TAN / COT
+  QS_LAYER_ROT     = 0,   // sign, phase table, per factor none / TAN / SHEAR3
   QS_LAYER_GENERAL = 1,   // sign, phase table, per factor none / any complex 2x2 (8 doubles)
   QS_LAYER_DENSE   = 2    // sign, then one dense 2^r x 2^r complex matrix, or two 4x4 blocks on factors
                           // (0,1) and (2,3) of a 4-bit step (QS_LH_PAIR); only gate layer of its step
